@@ -1,0 +1,195 @@
+/* kwb200 — C ABI of the B200-native Whisper transcription hot path (libkwb200.so).
+ *
+ * The reference (kotoba-tech/kotoba-whisper) has no native code and no FFI: its hot path is three Python calls into
+ * `transformers`.  Each entry point below names the Python interface it stands behind; the Python drop-in
+ * (kotoba_whisper_b200/) binds these with ctypes and re-exposes the reference's call surface unchanged.
+ *
+ *   kw_logmel            <- WhisperFeatureExtractor.__call__ / _torch_extract_fbank_features
+ *                           (HF/models/whisper/feature_extraction_whisper.py:189-342, 135-164; called from
+ *                            run_pseudo_labelling.py:268, run_data_filtering.py:338, HF pipelines/automatic_speech_recognition.py:67-72)
+ *   kw_encode            <- WhisperEncoder.forward (HF/models/whisper/modeling_whisper.py:593-647), reached from
+ *                           generate() via GenerationMixin._prepare_encoder_decoder_kwargs_for_generation (generation/utils.py:765-804)
+ *   kw_cross_kv          <- cross-attention K/V build inside WhisperAttention.forward (modeling_whisper.py:326-336)
+ *   kw_decode_step       <- WhisperDecoder.forward with EncoderDecoderCache, one token (modeling_whisper.py:734-796, 449-506)
+ *                           + proj_out (:1081) + the three Whisper logits processors (generation/logits_process.py:1855-2043)
+ *                           + argmax / eos / pad bookkeeping of GenerationMixin._sample (generation/utils.py:2762-2805)
+ *   kw_greedy_pass       <- one GenerationMixin.generate call as issued by generate_with_fallback
+ *                           (HF/models/whisper/generation_whisper.py:1027): encoder output -> prompt prefill -> greedy loop
+ *   kw_attention         <- the attention plug-in seam, ALL_ATTENTION_FUNCTIONS[name](module, q, k, v, ...) as called at
+ *                           modeling_whisper.py:342-352 (what `attn_implementation="sdpa"|"flash_attention_2"` selects,
+ *                           run_pseudo_labelling.py:64,230)
+ *
+ * Conventions: every pointer marked `dev` is a device pointer owned by the caller (torch tensors in the Python host);
+ * nothing is allocated per call (workspaces and KV pools are created in kw_model_create for `max_batch`); every call
+ * enqueues work on the given stream and does NOT synchronise unless stated; functions return 0 on success or a
+ * negative kw_status, with a message available from kw_last_error(); no exceptions cross the ABI; a model handle is
+ * not thread-safe (one host thread per GPU process, as under `accelerate launch`).
+ */
+#ifndef KWB200_H
+#define KWB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* kw_stream; /* cudaStream_t */
+
+typedef enum { KW_OK = 0, KW_ERR_ARG = -1, KW_ERR_CUDA = -2, KW_ERR_UNSUPPORTED = -3, KW_ERR_NOMEM = -4 } kw_status;
+typedef enum { KW_F32 = 0, KW_BF16 = 1 } kw_dtype;
+
+/* Model dimensions = the WhisperConfig fields the path reads (HF/models/whisper/configuration_whisper.py). */
+typedef struct {
+  int32_t vocab_size;      /* 51866 */
+  int32_t n_mels;          /* 128 (80 for v1/v2-era checkpoints) */
+  int32_t d_model;         /* 1280; multiple of 64 */
+  int32_t n_heads;         /* 20;  d_model / n_heads must be 64 */
+  int32_t ffn_dim;         /* 5120 */
+  int32_t enc_layers;      /* 32 */
+  int32_t dec_layers;      /* 2 (kotoba / distil) or 32 (teacher) */
+  int32_t max_source_pos;  /* 1500 */
+  int32_t max_target_pos;  /* 448 */
+  int32_t dtype;           /* kw_dtype of weight matrices, activations and KV caches; accumulation is always fp32 */
+  int32_t max_batch;       /* workspaces are sized for this many 30 s windows */
+} kw_config;
+
+/* Weight table: device pointers into caller-owned tensors, already in kernel layout (the Python repacker builds it
+ * from an HF state_dict, names in SURVEY.md §8b).  Matrices are `dtype` ([out, in] row-major like nn.Linear);
+ * biases, LayerNorm parameters and position tables are always fp32. */
+typedef struct {
+  const float *ln1_w, *ln1_b; /* self_attn_layer_norm */
+  const void* wqkv;           /* [3d, d] = [q*0.125 ; k ; v]  (the 1/sqrt(64) q scale is folded in: exact, power of 2) */
+  const float* bqkv;          /* [3d]    = [bq*0.125 ; 0 ; bv] (k_proj has no bias, modeling_whisper.py:279) */
+  const void* wo;             /* [d, d] */
+  const float* bo;
+  const float *ln2_w, *ln2_b; /* final_layer_norm */
+  const void* w1;             /* [ffn, d] */
+  const float* b1;
+  const void* w2;             /* [d, ffn] */
+  const float* b2;
+} kw_enc_layer_weights;
+
+typedef struct {
+  const float *ln1_w, *ln1_b; /* self_attn_layer_norm */
+  const void* wqkv;           /* [3d, d], q pre-scaled as above */
+  const float* bqkv;
+  const void* wo;
+  const float* bo;
+  const float *lnx_w, *lnx_b; /* encoder_attn_layer_norm */
+  const void* wq_x;           /* [d, d] cross-attention q (pre-scaled) */
+  const float* bq_x;
+  const void* wkv_x;          /* [2d, d] = [k ; v] applied to the encoder output once per pass */
+  const float* bkv_x;         /* [2d]    = [0 ; bv] */
+  const void* wo_x;
+  const float* bo_x;
+  const float *ln3_w, *ln3_b; /* final_layer_norm */
+  const void* w1;
+  const float* b1;
+  const void* w2;
+  const float* b2;
+} kw_dec_layer_weights;
+
+typedef struct {
+  const void* conv1_w;  /* [d, 3*n_mels], column = tap*n_mels + mel   (from conv1.weight [d, n_mels, 3]) */
+  const float* conv1_b;
+  const void* conv2_w;  /* [d, 3*d],      column = tap*d + channel    (from conv2.weight [d, d, 3]) */
+  const float* conv2_b;
+  const float* enc_pos; /* [max_source_pos, d] sinusoid table (embed_positions.weight) */
+  const float *enc_ln_w, *enc_ln_b;
+  const void* tok_embed; /* [vocab, d]; also proj_out (tied, modeling_whisper.py:966) */
+  const float* dec_pos;  /* [max_target_pos, d] learned */
+  const float *dec_ln_w, *dec_ln_b;
+  const kw_enc_layer_weights* enc; /* host array [enc_layers] */
+  const kw_dec_layer_weights* dec; /* host array [dec_layers] */
+} kw_weights;
+
+/* Token rules = the GenerationConfig fields read by the three processors and by _sample. */
+typedef struct {
+  int32_t eos_token_id;                /* 50257 */
+  int32_t pad_token_id;                /* 50257 */
+  int32_t no_timestamps_token_id;      /* 50364; timestamp_begin = this + 1 */
+  int32_t max_initial_timestamp_index; /* 50; < 0 = None */
+  const int32_t* suppress_tokens;      /* host array */
+  int32_t n_suppress;
+  const int32_t* begin_suppress_tokens; /* host array */
+  int32_t n_begin_suppress;
+} kw_token_rules;
+
+typedef struct kw_model kw_model;
+
+const char* kw_last_error(void);
+const char* kw_version(void);
+
+/* ---- log-mel ---------------------------------------------------------------------------------------------------
+ * audio  dev f32 [B, n_samples]   clip b occupies audio[b*n_samples ...]; samples >= lens[b] are read as 0 (right pad)
+ * lens   dev i32 [B] or NULL      (NULL: every clip is n_samples long)
+ * out    dev f32 [B, n_mels, n_samples/160]   (mel-major, time contiguous — HF's `input_features` layout;
+ *                                               n_samples/160 rounds down: HF computes 1 + n/160 frames and drops the last)
+ * n_samples >= 400; n_mels <= 128 with n_mels * (n_samples/160) a multiple of 4 (80 and 128 always qualify).
+ * clip_max dev f32 [B] scratch (per-clip max of log10 mel), overwritten. */
+int kw_logmel(const float* audio, const int32_t* lens, int32_t B, int32_t n_samples, int32_t n_mels, float* out,
+              float* clip_max, kw_stream stream);
+/* Slaney filterbank as the kernel uses it, float64 [201, n_mels] row-major, written to a HOST buffer (test hook). */
+int kw_mel_filterbank(int32_t n_mels, double* out_host);
+
+/* ---- model ------------------------------------------------------------------------------------------------------ */
+int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_rules* rules, kw_model** out);
+void kw_model_destroy(kw_model* m);
+/* bytes of device memory the handle allocated (workspaces + KV pools) */
+int64_t kw_model_workspace_bytes(const kw_model* m);
+
+/* mel dev f32 [B, n_mels, 2*max_source_pos] -> encoder output kept inside the handle; if enc_out (dev f32
+ * [B, max_source_pos, d]) is non-NULL a copy of the final-LayerNorm output is written there. */
+int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_stream stream);
+/* Use a caller-provided encoder output (generate(encoder_outputs=...)): dev f32 [B, max_source_pos, d]. */
+int kw_set_encoder_output(kw_model* m, const float* enc, int32_t B, kw_stream stream);
+/* Project the handle's encoder output to every decoder layer's cross-attention K/V pool. */
+int kw_cross_kv(kw_model* m, int32_t B, kw_stream stream);
+
+/* One decoder position for B rows.
+ * tokens dev i32 [B, ld_tokens]  token history: columns [0, pos] are read (column pos = the token fed in this step);
+ *                                when sample != 0 the chosen next token is written to column pos+1
+ * pos                            index of the fed token in the decoder sequence (0 = <|startoftranscript|>)
+ * begin_index                    prompt length (first generated token is at column begin_index)
+ * sample                         0: only extend the KV cache (prompt prefill); 1: also logits -> processors -> argmax
+ * return_timestamps              enables the WhisperTimeStamp rules
+ * finished dev i32 [B]           row state (1 after eos was emitted; such rows emit pad); updated when sample != 0
+ * logits_out dev f32 [B, vocab] or NULL   raw (unprocessed) fp32 logits of this step, for parity tests */
+int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos, int32_t begin_index,
+                   int32_t sample, int32_t return_timestamps, int32_t* finished, float* logits_out, kw_stream stream);
+
+/* Whole greedy pass on the handle's current encoder output (kw_encode / kw_set_encoder_output must have run):
+ * cross K/V, prefill of `n_prompt` prompt tokens (host array), then greedy steps until every row has emitted eos or
+ * the sequence length reaches max_length.  tokens dev i32 [B, max_length] receives prompt + generated ids (pad after
+ * eos).  Synchronises the stream every `check_every` steps to test the all-finished flag (0 = never, run to
+ * max_length).  Returns the number of decoder positions evaluated (>= 0) or a negative kw_status. */
+int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
+                   int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream);
+
+/* ---- attention seam ------------------------------------------------------------------------------------------------
+ * q,k,v dev [B, T, 3?]: strided views, element (b, t, h, e) at  ptr + b*stride_b + t*stride_t + h*64 + e ; head dim 64,
+ * softmax(q k^T) v with q pre-scaled (scaling = 1.0 at modeling_whisper.py:349), no mask.  out dev [B, Tq, H*64]. */
+int kw_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tq, int32_t Tk,
+                 int64_t q_stride_b, int64_t q_stride_t, int64_t kv_stride_b, int64_t kv_stride_t, int64_t o_stride_b,
+                 int64_t o_stride_t, int32_t dtype, kw_stream stream);
+
+/* ---- building blocks exported for the parity tests -------------------------------------------------------------- */
+/* out[M,N] = epilogue(A[M,K] . W[N,K]^T + bias); epi: 0 store, 1 gelu, 2 out(f32) += ; impl: 0 auto, 1 simt, 2 tcgen05 */
+int kw_linear(const void* A, const void* W, const float* bias, void* out, int32_t M, int32_t N, int32_t K, int32_t epi,
+              int32_t a_dtype, int32_t w_dtype, int32_t out_dtype, int32_t impl, kw_stream stream);
+int kw_layernorm(const float* x, const float* w, const float* b, void* out, int32_t rows, int32_t d, int32_t out_dtype,
+                 kw_stream stream);
+/* processors + argmax on given fp32 logits (same kernel kw_decode_step uses) */
+int kw_sample(kw_model* m, const float* logits, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos,
+              int32_t begin_index, int32_t return_timestamps, int32_t* finished, kw_stream stream);
+
+/* 0: auto (tcgen05 where eligible), 1: force SIMT GEMMs, 2: force tcgen05 (error if ineligible). Process-wide. */
+void kw_set_gemm_impl(int32_t impl);
+/* counts kernels launched by this library since the last reset (bench.py's gpu_launches) */
+int64_t kw_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KWB200_H */

@@ -1,0 +1,386 @@
+// C ABI of libkwb200.so (include/kwb200.h): model handle, workspace pools and the kernel schedules for the encoder,
+// the one-shot cross-K/V projection, a decoder step and a whole greedy pass.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "common.cuh"
+
+namespace kw {
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[1024] = "";
+static std::atomic<int> g_gemm_impl{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// kernels defined in the other translation units
+int logmel_launch(const float* audio, const int32_t* lens, int B, int n_samples, int n_mels, float* out,
+                  float* clip_max, cudaStream_t st);
+void mel_filterbank_f64(int n_mels, std::vector<double>& fb);
+int im2col_conv1(const float* mel, void* A1, int B, int C, int Tn, kw_dtype t, cudaStream_t st);
+int im2col_conv2(const void* h0, void* A2, int B, int d, int Tin, int Tout, kw_dtype t, cudaStream_t st);
+int layernorm(const float* x, const float* w, const float* b, void* out, int rows, int d, kw_dtype t, cudaStream_t st);
+int embed(const int* tokens, int ld_tokens, int pos, const void* E, const float* P, float* x, int B, int d, int vocab,
+          kw_dtype t, cudaStream_t st);
+int convert_f32_to(const float* in, void* out, size_t n, kw_dtype t, cudaStream_t st);
+int attention_simt(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk,
+                   long long q_sb, long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st,
+                   kw_dtype t, cudaStream_t st);
+int attention_tc(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, long long q_sb,
+                 long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st, cudaStream_t st);
+int dec_self_attn(const float* qkv, void* kc, void* vc, float* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
+                  cudaStream_t st);
+int dec_cross_attn(const float* q, const void* xkv, float* out, int B, int d, int H, int S, kw_dtype t, cudaStream_t st);
+int sample_launch(const float* logits, const unsigned char* flags, const SampleRules& r, int* tokens, int ld_tokens,
+                  int B, int pos, int begin_index, int return_ts, int* finished, cudaStream_t st);
+
+int gemm(const GemmArgs& g, cudaStream_t st) {
+  const int impl = g_gemm_impl.load();
+  if (impl != 1 && g.a_type == KW_BF16 && g.w_type == KW_BF16) {
+    int rc = gemm_tc(g, st);
+    if (rc != KW_ERR_UNSUPPORTED) return rc;
+    if (impl == 2) return rc;
+  } else if (impl == 2) {
+    set_error("gemm: tcgen05 path forced but operands are not bf16");
+    return KW_ERR_UNSUPPORTED;
+  }
+  return gemm_simt(g, st);
+}
+
+static size_t esize(kw_dtype t) { return t == KW_BF16 ? 2 : 4; }
+
+}  // namespace kw
+
+using namespace kw;
+
+struct kw_model {
+  kw_config cfg;
+  kw_weights w;
+  std::vector<kw_enc_layer_weights> enc;
+  std::vector<kw_dec_layer_weights> dec;
+  SampleRules rules;
+  kw_dtype t;
+  // device pools
+  char* pool = nullptr;
+  size_t pool_bytes = 0;
+  unsigned char* flags = nullptr;  // [vocab] bit0 = suppress, bit1 = suppress at begin
+  // encoder workspaces
+  void *bufP = nullptr, *bufQ = nullptr, *a = nullptr, *o = nullptr, *enc_out = nullptr;
+  float* x = nullptr;
+  // decoder workspaces
+  float *dx = nullptr, *da = nullptr, *dqkv = nullptr, *dq = nullptr, *dattn = nullptr, *dh = nullptr, *logits = nullptr;
+  void* self_k = nullptr;  // [L][B][H][max_t][64]
+  void* self_v = nullptr;
+  void* xkv = nullptr;  // [L][B*S][2d]
+  int* finished = nullptr;
+  int* finished_host = nullptr;  // pinned
+  int enc_B = 0;
+};
+
+extern "C" {
+
+const char* kw_last_error(void) { return g_err; }
+const char* kw_version(void) { return "kwb200 0.1 (sm_100a)"; }
+void kw_set_gemm_impl(int32_t impl) { g_gemm_impl.store(impl); }
+int64_t kw_launch_count(int32_t reset) {
+  long long v = g_launches.load();
+  if (reset) g_launches.store(0);
+  return v;
+}
+
+int kw_logmel(const float* audio, const int32_t* lens, int32_t B, int32_t n_samples, int32_t n_mels, float* out,
+              float* clip_max, kw_stream stream) {
+  KW_REQUIRE(audio && out && clip_max, "kw_logmel: null pointer");
+  return logmel_launch(audio, lens, B, n_samples, n_mels, out, clip_max, (cudaStream_t)stream);
+}
+
+int kw_mel_filterbank(int32_t n_mels, double* out_host) {
+  KW_REQUIRE(n_mels > 0 && n_mels <= 128 && out_host, "kw_mel_filterbank: bad arguments");
+  std::vector<double> fb;
+  mel_filterbank_f64(n_mels, fb);
+  memcpy(out_host, fb.data(), fb.size() * sizeof(double));
+  return KW_OK;
+}
+
+int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_rules* rules, kw_model** out) {
+  KW_REQUIRE(cfg && w && rules && out, "kw_model_create: null argument");
+  KW_REQUIRE(cfg->d_model % 64 == 0 && cfg->n_heads * 64 == cfg->d_model, "kw_model_create: head dim must be 64");
+  KW_REQUIRE(cfg->ffn_dim % 16 == 0 && (3 * cfg->n_mels) % 16 == 0, "kw_model_create: ffn / 3*n_mels must be multiples of 16");
+  KW_REQUIRE(cfg->max_batch >= 1 && cfg->max_target_pos <= 512, "kw_model_create: bad max_batch / max_target_pos");
+  KW_REQUIRE(cfg->dtype == KW_F32 || cfg->dtype == KW_BF16, "kw_model_create: bad dtype");
+  kw_model* m = new kw_model();
+  m->cfg = *cfg;
+  m->w = *w;
+  m->enc.assign(w->enc, w->enc + cfg->enc_layers);
+  m->dec.assign(w->dec, w->dec + cfg->dec_layers);
+  m->w.enc = m->enc.data();
+  m->w.dec = m->dec.data();
+  m->t = (kw_dtype)cfg->dtype;
+  m->rules = {rules->eos_token_id, rules->pad_token_id, rules->no_timestamps_token_id,
+              rules->no_timestamps_token_id + 1, rules->max_initial_timestamp_index, cfg->vocab_size};
+
+  const size_t B = cfg->max_batch, d = cfg->d_model, S = cfg->max_source_pos, T2 = 2 * S, F = cfg->ffn_dim;
+  const size_t V = cfg->vocab_size, L = cfg->dec_layers, es = esize(m->t);
+  auto al = [](size_t n) { return (n + 255) / 256 * 256; };
+  const size_t szP = al(std::max(std::max(B * T2 * 3 * cfg->n_mels, B * S * 3 * d), B * S * 3 * d) * es);
+  const size_t szQ = al(std::max(B * T2 * d, B * S * F) * es);
+  const size_t szA = al(B * S * d * es), szX = al(B * S * d * 4);
+  const size_t szSelf = al(L * B * d * cfg->max_target_pos * es), szXkv = al(L * B * S * 2 * d * es);
+  const size_t szDec = al(B * d * 4), szDqkv = al(B * 3 * d * 4), szDh = al(B * F * 4), szLog = al(B * V * 4);
+  const size_t total = szP + szQ + 3 * szA + szX + 2 * szSelf + szXkv + 4 * szDec + szDqkv + szDh + szLog + al(V) +
+                       al(B * 4);
+  cudaError_t e = cudaMalloc(&m->pool, total);
+  if (e != cudaSuccess) {
+    set_error("kw_model_create: cudaMalloc(%zu bytes) failed: %s", total, cudaGetErrorString(e));
+    delete m;
+    return KW_ERR_NOMEM;
+  }
+  m->pool_bytes = total;
+  char* p = m->pool;
+  auto take = [&](size_t n) { char* r = p; p += n; return (void*)r; };
+  m->bufP = take(szP); m->bufQ = take(szQ);
+  m->a = take(szA); m->o = take(szA); m->enc_out = take(szA);
+  m->x = (float*)take(szX);
+  m->self_k = take(szSelf); m->self_v = take(szSelf); m->xkv = take(szXkv);
+  m->dx = (float*)take(szDec); m->da = (float*)take(szDec); m->dq = (float*)take(szDec); m->dattn = (float*)take(szDec);
+  m->dqkv = (float*)take(szDqkv); m->dh = (float*)take(szDh); m->logits = (float*)take(szLog);
+  m->flags = (unsigned char*)take(al(V));
+  m->finished = (int*)take(al(B * 4));
+
+  std::vector<unsigned char> hf(V, 0);
+  for (int i = 0; i < rules->n_suppress; ++i) {
+    int t = rules->suppress_tokens[i];
+    if (t >= 0 && (size_t)t < V) hf[t] |= 1;
+  }
+  for (int i = 0; i < rules->n_begin_suppress; ++i) {
+    int t = rules->begin_suppress_tokens[i];
+    if (t >= 0 && (size_t)t < V) hf[t] |= 2;
+  }
+  if (cudaMemcpy(m->flags, hf.data(), V, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMallocHost(&m->finished_host, B * sizeof(int)) != cudaSuccess) {
+    set_error("kw_model_create: flag upload / pinned alloc failed");
+    cudaFree(m->pool);
+    delete m;
+    return KW_ERR_CUDA;
+  }
+  *out = m;
+  return KW_OK;
+}
+
+void kw_model_destroy(kw_model* m) {
+  if (!m) return;
+  cudaFree(m->pool);
+  if (m->finished_host) cudaFreeHost(m->finished_host);
+  delete m;
+}
+
+int64_t kw_model_workspace_bytes(const kw_model* m) { return m ? (int64_t)m->pool_bytes : 0; }
+
+static GemmArgs mk(const void* A, int lda, kw_dtype at, const void* W, kw_dtype wt, const float* bias, void* out,
+                   int ldo, kw_dtype ot, int M, int N, int K, int epi) {
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.W = W; g.bias = bias; g.out = out;
+  g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldo = ldo;
+  g.epi = epi; g.a_type = at; g.w_type = wt; g.out_type = ot;
+  return g;
+}
+
+#define KW_TRY(expr)           \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != KW_OK) return _rc; \
+  } while (0)
+
+int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_stream stream) {
+  KW_REQUIRE(m && mel, "kw_encode: null argument");
+  KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch, "kw_encode: B=%d outside [1, max_batch=%d]", B, m->cfg.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const kw_config& c = m->cfg;
+  const kw_dtype t = m->t;
+  const int d = c.d_model, S = c.max_source_pos, T2 = 2 * S, F = c.ffn_dim, M = B * S;
+  // conv stem as two im2col GEMMs (modeling_whisper.py:619-625)
+  KW_TRY(im2col_conv1(mel, m->bufP, B, c.n_mels, T2, t, st));
+  KW_TRY(gemm(mk(m->bufP, 3 * c.n_mels, t, m->w.conv1_w, t, m->w.conv1_b, m->bufQ, d, t, B * T2, d, 3 * c.n_mels, EPI_GELU), st));
+  KW_TRY(im2col_conv2(m->bufQ, m->bufP, B, d, T2, S, t, st));
+  {
+    GemmArgs g = mk(m->bufP, 3 * d, t, m->w.conv2_w, t, m->w.conv2_b, m->x, d, KW_F32, M, d, 3 * d, EPI_GELU_POS);
+    g.pos = m->w.enc_pos;
+    g.pos_period = S;
+    KW_TRY(gemm(g, st));
+  }
+  for (int l = 0; l < c.enc_layers; ++l) {
+    const kw_enc_layer_weights& w = m->enc[l];
+    KW_TRY(layernorm(m->x, w.ln1_w, w.ln1_b, m->a, M, d, t, st));
+    KW_TRY(gemm(mk(m->a, d, t, w.wqkv, t, w.bqkv, m->bufP, 3 * d, t, M, 3 * d, d, EPI_STORE), st));
+    {
+      const char* qkv = (const char*)m->bufP;
+      const size_t es = esize(t);
+      int rc = KW_ERR_UNSUPPORTED;
+      if (t == KW_BF16 && g_gemm_impl.load() != 1)
+        rc = attention_tc(qkv, qkv + d * es, qkv + 2 * d * es, m->o, B, c.n_heads, S, S, (long long)S * 3 * d, 3 * d,
+                          (long long)S * 3 * d, 3 * d, (long long)S * d, d, st);
+      if (rc == KW_ERR_UNSUPPORTED)
+        rc = attention_simt(qkv, qkv + d * es, qkv + 2 * d * es, m->o, B, c.n_heads, S, S, (long long)S * 3 * d, 3 * d,
+                            (long long)S * 3 * d, 3 * d, (long long)S * d, d, t, st);
+      KW_TRY(rc);
+    }
+    KW_TRY(gemm(mk(m->o, d, t, w.wo, t, w.bo, m->x, d, KW_F32, M, d, d, EPI_RESID), st));
+    KW_TRY(layernorm(m->x, w.ln2_w, w.ln2_b, m->a, M, d, t, st));
+    KW_TRY(gemm(mk(m->a, d, t, w.w1, t, w.b1, m->bufQ, F, t, M, F, d, EPI_GELU), st));
+    KW_TRY(gemm(mk(m->bufQ, F, t, w.w2, t, w.b2, m->x, d, KW_F32, M, d, F, EPI_RESID), st));
+  }
+  KW_TRY(layernorm(m->x, m->w.enc_ln_w, m->w.enc_ln_b, m->enc_out, M, d, t, st));
+  if (enc_out) KW_TRY(layernorm(m->x, m->w.enc_ln_w, m->w.enc_ln_b, enc_out, M, d, KW_F32, st));
+  m->enc_B = B;
+  return KW_OK;
+}
+
+int kw_set_encoder_output(kw_model* m, const float* enc, int32_t B, kw_stream stream) {
+  KW_REQUIRE(m && enc && B >= 1 && B <= m->cfg.max_batch, "kw_set_encoder_output: bad arguments");
+  KW_TRY(convert_f32_to(enc, m->enc_out, (size_t)B * m->cfg.max_source_pos * m->cfg.d_model, m->t, (cudaStream_t)stream));
+  m->enc_B = B;
+  return KW_OK;
+}
+
+int kw_cross_kv(kw_model* m, int32_t B, kw_stream stream) {
+  KW_REQUIRE(m && B >= 1 && B <= m->enc_B, "kw_cross_kv: B=%d but encoder output holds %d rows", B, m ? m->enc_B : 0);
+  const kw_config& c = m->cfg;
+  const int d = c.d_model, S = c.max_source_pos;
+  const size_t layer_stride = (size_t)c.max_batch * S * 2 * d * esize(m->t);
+  for (int l = 0; l < c.dec_layers; ++l) {
+    const kw_dec_layer_weights& w = m->dec[l];
+    KW_TRY(gemm(mk(m->enc_out, d, m->t, w.wkv_x, m->t, w.bkv_x, (char*)m->xkv + l * layer_stride, 2 * d, m->t, B * S, 2 * d,
+                   d, EPI_STORE), (cudaStream_t)stream));
+  }
+  return KW_OK;
+}
+
+static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int B, int pos, cudaStream_t st) {
+  const kw_config& c = m->cfg;
+  const kw_dtype t = m->t;
+  const int d = c.d_model, S = c.max_source_pos, F = c.ffn_dim, H = c.n_heads, MT = c.max_target_pos;
+  const size_t self_stride = (size_t)c.max_batch * d * MT * esize(t);
+  const size_t xkv_stride = (size_t)c.max_batch * S * 2 * d * esize(t);
+  KW_TRY(embed(tokens, ld_tokens, pos, m->w.tok_embed, m->w.dec_pos, m->dx, B, d, c.vocab_size, t, st));
+  for (int l = 0; l < c.dec_layers; ++l) {
+    const kw_dec_layer_weights& w = m->dec[l];
+    KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, KW_F32, st));
+    KW_TRY(gemm(mk(m->da, d, KW_F32, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
+    KW_TRY(dec_self_attn(m->dqkv, (char*)m->self_k + l * self_stride, (char*)m->self_v + l * self_stride, m->dattn, B, d,
+                         H, MT, pos, t, st));
+    KW_TRY(gemm(mk(m->dattn, d, KW_F32, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+    KW_TRY(layernorm(m->dx, w.lnx_w, w.lnx_b, m->da, B, d, KW_F32, st));
+    KW_TRY(gemm(mk(m->da, d, KW_F32, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), st));
+    KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st));
+    KW_TRY(gemm(mk(m->dattn, d, KW_F32, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+    KW_TRY(layernorm(m->dx, w.ln3_w, w.ln3_b, m->da, B, d, KW_F32, st));
+    KW_TRY(gemm(mk(m->da, d, KW_F32, w.w1, t, w.b1, m->dh, F, KW_F32, B, F, d, EPI_GELU), st));
+    KW_TRY(gemm(mk(m->dh, F, KW_F32, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), st));
+  }
+  return KW_OK;
+}
+
+int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos, int32_t begin_index,
+                   int32_t sample, int32_t return_timestamps, int32_t* finished, float* logits_out, kw_stream stream) {
+  KW_REQUIRE(m && tokens, "kw_decode_step: null argument");
+  KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch && pos >= 0 && pos < m->cfg.max_target_pos && pos < ld_tokens,
+             "kw_decode_step: B=%d pos=%d ld=%d out of range", B, pos, ld_tokens);
+  cudaStream_t st = (cudaStream_t)stream;
+  const kw_config& c = m->cfg;
+  KW_TRY(decode_hidden(m, tokens, ld_tokens, B, pos, st));
+  if (!sample && !logits_out) return KW_OK;
+  KW_TRY(layernorm(m->dx, m->w.dec_ln_w, m->w.dec_ln_b, m->da, B, c.d_model, KW_F32, st));
+  float* lg = logits_out ? logits_out : m->logits;
+  KW_TRY(gemm(mk(m->da, c.d_model, KW_F32, m->w.tok_embed, m->t, nullptr, lg, c.vocab_size, KW_F32, B, c.vocab_size,
+                 c.d_model, EPI_STORE), st));
+  if (sample) {
+    KW_REQUIRE(finished, "kw_decode_step: sample requires the finished array");
+    KW_TRY(sample_launch(lg, m->flags, m->rules, tokens, ld_tokens, B, pos, begin_index, return_timestamps, finished, st));
+  }
+  return KW_OK;
+}
+
+int kw_sample(kw_model* m, const float* logits, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos,
+              int32_t begin_index, int32_t return_timestamps, int32_t* finished, kw_stream stream) {
+  KW_REQUIRE(m && logits && tokens && finished, "kw_sample: null argument");
+  return sample_launch(logits, m->flags, m->rules, tokens, ld_tokens, B, pos, begin_index, return_timestamps, finished,
+                       (cudaStream_t)stream);
+}
+
+__global__ void fill_prompt_kernel(int* tokens, int ld, int B, const int4 p0, int n_prompt, int pad, int* finished) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int pr[4] = {p0.x, p0.y, p0.z, p0.w};
+  for (int j = 0; j < ld; ++j) tokens[(size_t)b * ld + j] = j < n_prompt ? pr[j] : pad;
+  finished[b] = 0;
+}
+
+int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
+                   int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream) {
+  KW_REQUIRE(m && prompt && tokens, "kw_greedy_pass: null argument");
+  KW_REQUIRE(n_prompt >= 1 && n_prompt <= 4, "kw_greedy_pass: prompt of %d tokens (1..4 supported)", n_prompt);
+  KW_REQUIRE(max_length > n_prompt && max_length <= m->cfg.max_target_pos,
+             "kw_greedy_pass: max_length=%d must be in (%d, %d]", max_length, n_prompt, m->cfg.max_target_pos);
+  KW_REQUIRE(B >= 1 && B <= m->enc_B, "kw_greedy_pass: B=%d but encoder output holds %d rows", B, m->enc_B);
+  cudaStream_t st = (cudaStream_t)stream;
+  int4 p0 = make_int4(prompt[0], n_prompt > 1 ? prompt[1] : 0, n_prompt > 2 ? prompt[2] : 0, n_prompt > 3 ? prompt[3] : 0);
+  fill_prompt_kernel<<<ceil_div(B, 128), 128, 0, st>>>(tokens, max_length, B, p0, n_prompt, m->rules.pad, m->finished);
+  KW_LAUNCH_OK();
+  ++g_launches;
+  KW_TRY(kw_cross_kv(m, B, stream));
+  int steps = 0;
+  for (int pos = 0; pos + 1 < max_length; ++pos) {
+    const int sample = pos >= n_prompt - 1;
+    KW_TRY(kw_decode_step(m, tokens, max_length, B, pos, n_prompt, sample, return_timestamps, m->finished, nullptr, stream));
+    ++steps;
+    const int generated = pos + 2 - n_prompt;  // tokens sampled so far
+    if (check_every > 0 && sample && generated % check_every == 0 && pos + 2 < max_length) {
+      KW_CUDA_OK(cudaMemcpyAsync(m->finished_host, m->finished, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+      KW_CUDA_OK(cudaStreamSynchronize(st));
+      bool all = true;
+      for (int b = 0; b < B; ++b) all = all && m->finished_host[b];
+      if (all) break;
+    }
+  }
+  return steps;
+}
+
+int kw_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tq, int32_t Tk,
+                 int64_t q_stride_b, int64_t q_stride_t, int64_t kv_stride_b, int64_t kv_stride_t, int64_t o_stride_b,
+                 int64_t o_stride_t, int32_t dtype, kw_stream stream) {
+  KW_REQUIRE(q && k && v && out, "kw_attention: null pointer");
+  if (dtype == KW_BF16 && g_gemm_impl.load() != 1) {
+    int rc = attention_tc(q, k, v, out, B, H, Tq, Tk, q_stride_b, q_stride_t, kv_stride_b, kv_stride_t, o_stride_b,
+                          o_stride_t, (cudaStream_t)stream);
+    if (rc != KW_ERR_UNSUPPORTED) return rc;
+  }
+  return attention_simt(q, k, v, out, B, H, Tq, Tk, q_stride_b, q_stride_t, kv_stride_b, kv_stride_t, o_stride_b,
+                        o_stride_t, (kw_dtype)dtype, (cudaStream_t)stream);
+}
+
+int kw_linear(const void* A, const void* W, const float* bias, void* out, int32_t M, int32_t N, int32_t K, int32_t epi,
+              int32_t a_dtype, int32_t w_dtype, int32_t out_dtype, int32_t impl, kw_stream stream) {
+  KW_REQUIRE(A && W && out && epi >= 0 && epi <= 2, "kw_linear: bad arguments");
+  GemmArgs g = mk(A, K, (kw_dtype)a_dtype, W, (kw_dtype)w_dtype, bias, out, N, (kw_dtype)out_dtype, M, N, K, epi);
+  if (impl == 1) return gemm_simt(g, (cudaStream_t)stream);
+  if (impl == 2) return gemm_tc(g, (cudaStream_t)stream);
+  return gemm(g, (cudaStream_t)stream);
+}
+
+int kw_layernorm(const float* x, const float* w, const float* b, void* out, int32_t rows, int32_t d, int32_t out_dtype,
+                 kw_stream stream) {
+  KW_REQUIRE(x && w && b && out, "kw_layernorm: null pointer");
+  return layernorm(x, w, b, out, rows, d, (kw_dtype)out_dtype, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,368 @@
+// Attention kernels, head dim 64, fp32 arithmetic on fp32 / bf16 storage:
+//   * attn_simt_kernel        encoder self-attention (and the generic plug-in seam kw_attention): flash-style, online
+//                             softmax, no mask, q pre-scaled (modeling_whisper.py:310, 342-352)
+//   * dec_self_attn_kernel    one decoder position: append k,v to the preallocated self-KV pool, attend over 0..pos
+//                             (replaces DynamicLayer.update = torch.cat, HF/cache_utils.py:102-120)
+//   * dec_cross_attn_kernel   one decoder position over the 1500 cached encoder K/V rows (modeling_whisper.py:315-336);
+//                             this is the HBM-dominant kernel of a decode step
+#include <atomic>
+
+#include "common.cuh"
+
+namespace kw {
+
+extern std::atomic<long long> g_launches;
+
+constexpr int HD = 64;
+
+// accurate expf for fp32 storage (exact-mode parity), SFU ex2 for bf16 storage
+template <typename T> __device__ __forceinline__ float exp_t(float x);
+template <> __device__ __forceinline__ float exp_t<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ float exp_t<bf16>(float x) { return __expf(x); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Encoder attention.  CTA = (64-query tile, head, batch), 256 threads as 16 x 16: thread (ty, tx) owns queries
+// ty + 16 i and keys tx + 16 j (i, j < 4) of the 64 x 64 score tile, and output columns 4 tx .. 4 tx + 3.  The 16
+// threads sharing a query row sit in one half-warp, so the row max / sum are 4 shuffles and P only needs __syncwarp.
+constexpr int AT_BQ = 64, AT_BK = 64, AT_LD = HD + 4;  // +4 floats: rows stay 16 B aligned, LDS.128 conflict-free
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ out, int Tq,
+                 int Tk, long long q_sb, long long q_st, long long kv_sb, long long kv_st, long long o_sb,
+                 long long o_st) {
+  extern __shared__ __align__(16) float sm[];
+  float* Qs = sm;                      // [64][68]
+  float* Ks = Qs + AT_BQ * AT_LD;      // [64][68]
+  float* Vs = Ks + AT_BK * AT_LD;      // [64][68]
+  float* Ps = Vs + AT_BK * AT_LD;      // [64][68]
+
+  const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
+  const int q0 = blockIdx.x * AT_BQ, h = blockIdx.y, b = blockIdx.z;
+  const T* qb = q + (size_t)b * q_sb + (size_t)h * HD;
+  const T* kb = k + (size_t)b * kv_sb + (size_t)h * HD;
+  const T* vb = v + (size_t)b * kv_sb + (size_t)h * HD;
+
+  // 64 rows x 16 float4 per tile -> 4 float4 per thread
+  for (int i = tid; i < AT_BQ * (HD / 4); i += 256) {
+    int r = i / (HD / 4), c = (i % (HD / 4)) * 4;
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < Tq) val = ld4(qb + (size_t)(q0 + r) * q_st + c);
+    *reinterpret_cast<float4*>(Qs + r * AT_LD + c) = val;
+  }
+
+  float m_run[4], l_run[4];
+  float4 o_acc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -INFINITY;
+    l_run[i] = 0.0f;
+    o_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  for (int k0 = 0; k0 < Tk; k0 += AT_BK) {
+    __syncthreads();  // previous tile's Ks/Vs/Ps fully consumed (also covers the Qs fill)
+    for (int i = tid; i < AT_BK * (HD / 4); i += 256) {
+      int r = i / (HD / 4), c = (i % (HD / 4)) * 4;
+      float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f), vv4 = kv4;
+      if (k0 + r < Tk) {
+        kv4 = ld4(kb + (size_t)(k0 + r) * kv_st + c);
+        vv4 = ld4(vb + (size_t)(k0 + r) * kv_st + c);
+      }
+      *reinterpret_cast<float4*>(Ks + r * AT_LD + c) = kv4;
+      *reinterpret_cast<float4*>(Vs + r * AT_LD + c) = vv4;
+    }
+    __syncthreads();
+
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.0f;
+#pragma unroll 4
+    for (int d = 0; d < HD; d += 4) {
+      float4 qa[4], ka[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qa[i] = *reinterpret_cast<const float4*>(Qs + (ty + 16 * i) * AT_LD + d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ka[j] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * j) * AT_LD + d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[i][j] = fmaf(qa[i].x, ka[j].x, s[i][j]);
+          s[i][j] = fmaf(qa[i].y, ka[j].y, s[i][j]);
+          s[i][j] = fmaf(qa[i].z, ka[j].z, s[i][j]);
+          s[i][j] = fmaf(qa[i].w, ka[j].w, s[i][j]);
+        }
+    }
+    // online softmax per query row
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k0 + tx + 16 * j >= Tk) s[i][j] = -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_new = fmaxf(m_run[i], mx);  // finite: every tile has >= 1 valid key
+      const float corr = exp_t<T>(m_run[i] - m_new);
+      float rs = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float p = exp_t<T>(s[i][j] - m_new);
+        rs += p;
+        Ps[(ty + 16 * i) * AT_LD + tx + 16 * j] = p;
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+      l_run[i] = l_run[i] * corr + rs;
+      m_run[i] = m_new;
+      o_acc[i].x *= corr; o_acc[i].y *= corr; o_acc[i].z *= corr; o_acc[i].w *= corr;
+    }
+    __syncwarp();  // P rows of this half-warp are written and read by the same half-warp
+#pragma unroll 4
+    for (int kk = 0; kk < AT_BK; kk += 4) {
+      float4 pa[4], va[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pa[i] = *reinterpret_cast<const float4*>(Ps + (ty + 16 * i) * AT_LD + kk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) va[j] = *reinterpret_cast<const float4*>(Vs + (kk + j) * AT_LD + 4 * tx);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        o_acc[i].x = fmaf(pa[i].x, va[0].x, o_acc[i].x); o_acc[i].y = fmaf(pa[i].x, va[0].y, o_acc[i].y);
+        o_acc[i].z = fmaf(pa[i].x, va[0].z, o_acc[i].z); o_acc[i].w = fmaf(pa[i].x, va[0].w, o_acc[i].w);
+        o_acc[i].x = fmaf(pa[i].y, va[1].x, o_acc[i].x); o_acc[i].y = fmaf(pa[i].y, va[1].y, o_acc[i].y);
+        o_acc[i].z = fmaf(pa[i].y, va[1].z, o_acc[i].z); o_acc[i].w = fmaf(pa[i].y, va[1].w, o_acc[i].w);
+        o_acc[i].x = fmaf(pa[i].z, va[2].x, o_acc[i].x); o_acc[i].y = fmaf(pa[i].z, va[2].y, o_acc[i].y);
+        o_acc[i].z = fmaf(pa[i].z, va[2].z, o_acc[i].z); o_acc[i].w = fmaf(pa[i].z, va[2].w, o_acc[i].w);
+        o_acc[i].x = fmaf(pa[i].w, va[3].x, o_acc[i].x); o_acc[i].y = fmaf(pa[i].w, va[3].y, o_acc[i].y);
+        o_acc[i].z = fmaf(pa[i].w, va[3].z, o_acc[i].z); o_acc[i].w = fmaf(pa[i].w, va[3].w, o_acc[i].w);
+      }
+    }
+  }
+
+  T* ob = out + (size_t)b * o_sb + (size_t)h * HD;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = q0 + ty + 16 * i;
+    if (r < Tq) {
+      const float inv = 1.0f / l_run[i];
+      st4(ob + (size_t)r * o_st + 4 * tx,
+          make_float4(o_acc[i].x * inv, o_acc[i].y * inv, o_acc[i].z * inv, o_acc[i].w * inv));
+    }
+  }
+}
+
+int attention_simt(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk,
+                   long long q_sb, long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st,
+                   kw_dtype t, cudaStream_t st) {
+  KW_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
+  KW_REQUIRE(q_st % 4 == 0 && kv_st % 4 == 0 && o_st % 4 == 0 && q_sb % 4 == 0 && kv_sb % 4 == 0 && o_sb % 4 == 0,
+             "attention: strides must be multiples of 4 elements");
+  const size_t smem = sizeof(float) * 4 * AT_BQ * AT_LD;
+  static bool attr = false;
+  if (!attr) {
+    KW_CUDA_OK(cudaFuncSetAttribute(attn_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    KW_CUDA_OK(cudaFuncSetAttribute(attn_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid(ceil_div(Tq, AT_BQ), H, B);
+  if (t == KW_BF16)
+    attn_simt_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, Tq, Tk,
+                                                    q_sb, q_st, kv_sb, kv_st, o_sb, o_st);
+  else
+    attn_simt_kernel<float><<<grid, 256, smem, st>>>((const float*)q, (const float*)k, (const float*)v, (float*)out,
+                                                     Tq, Tk, q_sb, q_st, kv_sb, kv_st, o_sb, o_st);
+  KW_LAUNCH_OK();
+  ++g_launches;
+  return KW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decoder self-attention, one position.  qkv f32 [B, 3d] (q pre-scaled | k | v) from the fused projection;
+// pools kc/vc typed [B, H, max_t, 64].  CTA = (head, batch), 128 threads.
+template <typename T>
+__global__ void __launch_bounds__(128)
+dec_self_attn_kernel(const float* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc, float* __restrict__ out,
+                     int d, int H, int max_t, int pos) {
+  __shared__ float s_q[HD];
+  __shared__ float s_p[512];
+  __shared__ float s_red[4];
+  __shared__ float s_o[2][HD];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const float* row = qkv + (size_t)b * 3 * d;
+  T* kp = kc + ((size_t)b * H + h) * max_t * HD;
+  T* vp = vc + ((size_t)b * H + h) * max_t * HD;
+  if (tid < HD) {
+    s_q[tid] = row[h * HD + tid];
+    st_f(kp + (size_t)pos * HD + tid, row[d + h * HD + tid]);
+  } else {
+    st_f(vp + (size_t)pos * HD + (tid - HD), row[2 * d + h * HD + (tid - HD)]);
+  }
+  __syncthreads();  // the new k/v row is visible to the whole CTA (global writes by this CTA, read below by this CTA)
+  const int n = pos + 1;
+  float lmax = -INFINITY;
+  for (int j = tid; j < n; j += 128) {
+    const T* kr = kp + (size_t)j * HD;
+    float acc = 0.0f;
+#pragma unroll
+    for (int e = 0; e < HD; e += 4) {
+      float4 kk = ld4(kr + e);
+      acc = fmaf(s_q[e], kk.x, acc); acc = fmaf(s_q[e + 1], kk.y, acc);
+      acc = fmaf(s_q[e + 2], kk.z, acc); acc = fmaf(s_q[e + 3], kk.w, acc);
+    }
+    s_p[j] = acc;
+    lmax = fmaxf(lmax, acc);
+  }
+  lmax = warp_max(lmax);
+  if ((tid & 31) == 0) s_red[tid >> 5] = lmax;
+  __syncthreads();
+  const float mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  float lsum = 0.0f;
+  for (int j = tid; j < n; j += 128) {
+    float p = exp_t<T>(s_p[j] - mx);
+    s_p[j] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  if ((tid & 31) == 0) s_red[tid >> 5] = lsum;
+  __syncthreads();
+  const float inv = 1.0f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+  const int e = tid & 63, half = tid >> 6;
+  float acc = 0.0f;
+  for (int j = half; j < n; j += 2) acc = fmaf(s_p[j], ld_f(vp + (size_t)j * HD + e), acc);
+  s_o[half][e] = acc;
+  __syncthreads();
+  if (tid < HD) out[(size_t)b * d + h * HD + tid] = (s_o[0][tid] + s_o[1][tid]) * inv;
+}
+
+int dec_self_attn(const float* qkv, void* kc, void* vc, float* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
+                  cudaStream_t st) {
+  KW_REQUIRE(pos >= 0 && pos < max_t && max_t <= 512, "dec_self_attn: pos=%d max_t=%d", pos, max_t);
+  dim3 grid(H, B);
+  if (t == KW_BF16) dec_self_attn_kernel<bf16><<<grid, 128, 0, st>>>(qkv, (bf16*)kc, (bf16*)vc, out, d, H, max_t, pos);
+  else dec_self_attn_kernel<float><<<grid, 128, 0, st>>>(qkv, (float*)kc, (float*)vc, out, d, H, max_t, pos);
+  KW_LAUNCH_OK();
+  ++g_launches;
+  return KW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decoder cross-attention, one position.  q f32 [B, d] (pre-scaled); xkv typed [B*S, 2d] = [K | V] rows of the one-shot
+// projection (row stride 2d); out f32 [B, d].  CTA = (head, batch), 256 threads.  8 lanes share one key row with one
+// 16 B (bf16) / two 16 B (f32) loads each, so every K/V byte is fetched exactly once with full 32 B sectors.
+__device__ __forceinline__ void load8(const float* p, float* f) {
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float* f) {
+  uint4 r = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h2[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, float* __restrict__ out, int d, int S) {
+  extern __shared__ float s_p[];  // [S]
+  __shared__ float s_red[8];
+  __shared__ float s_o[8][HD];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, sub = lane >> 3, l8 = lane & 7;
+  const size_t ld = 2 * (size_t)d;
+  const T* kbase = xkv + (size_t)b * S * ld + (size_t)h * HD + l8 * 8;
+  const T* vbase = kbase + d;
+  float qf[8];
+  load8(q + (size_t)b * d + h * HD + l8 * 8, qf);
+
+  float lmax = -INFINITY;
+  for (int j0 = warp * 4; j0 < S; j0 += 32) {  // 8 warps x 4 keys per iteration
+    const int j = j0 + sub;
+    float acc = 0.0f;
+    if (j < S) {
+      float kf[8];
+      load8(kbase + (size_t)j * ld, kf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], kf[e], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    if (j < S) {
+      if (l8 == 0) s_p[j] = acc;
+      lmax = fmaxf(lmax, acc);
+    }
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) s_red[warp] = lmax;
+  __syncthreads();
+  float mx = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
+  __syncthreads();
+  float lsum = 0.0f;
+  for (int j = tid; j < S; j += 256) {
+    float p = exp_t<T>(s_p[j] - mx);
+    s_p[j] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) s_red[warp] = lsum;
+  __syncthreads();
+  float tot = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += s_red[i];
+  const float inv = 1.0f / tot;
+
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+  for (int j0 = warp * 4; j0 < S; j0 += 32) {
+    const int j = j0 + sub;
+    if (j < S) {
+      float vf[8];
+      load8(vbase + (size_t)j * ld, vf);
+      const float p = s_p[j];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = fmaf(p, vf[e], o[e]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_o[warp][l8 * 8 + e] = o[e];
+  }
+  __syncthreads();
+  if (tid < HD) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) acc += s_o[w][tid];
+    out[(size_t)b * d + h * HD + tid] = acc * inv;
+  }
+}
+
+int dec_cross_attn(const float* q, const void* xkv, float* out, int B, int d, int H, int S, kw_dtype t,
+                   cudaStream_t st) {
+  dim3 grid(H, B);
+  const size_t smem = sizeof(float) * S;
+  if (t == KW_BF16) dec_cross_attn_kernel<bf16><<<grid, 256, smem, st>>>(q, (const bf16*)xkv, out, d, S);
+  else dec_cross_attn_kernel<float><<<grid, 256, smem, st>>>(q, (const float*)xkv, out, d, S);
+  KW_LAUNCH_OK();
+  ++g_launches;
+  return KW_OK;
+}
+
+}  // namespace kw

@@ -1,0 +1,110 @@
+// Shared helpers for the kwb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/kwb200.h"
+
+namespace kw {
+
+typedef __nv_bfloat16 bf16;
+
+void set_error(const char* fmt, ...);
+
+#define KW_CUDA_OK(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      kw::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));     \
+      return KW_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define KW_LAUNCH_OK()                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) {                                                                  \
+      kw::set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));        \
+      return KW_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define KW_REQUIRE(cond, ...)                                                                 \
+  do {                                                                                        \
+    if (!(cond)) {                                                                            \
+      kw::set_error(__VA_ARGS__);                                                             \
+      return KW_ERR_ARG;                                                                      \
+    }                                                                                         \
+  } while (0)
+
+// ---- typed element access: storage type T in {float, bf16}, arithmetic always fp32 ---------------
+__device__ __forceinline__ float ld_f(const float* p) { return *p; }
+__device__ __forceinline__ float ld_f(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st_f(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_f(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 4 consecutive elements (pointer must be 16 B / 8 B aligned respectively)
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+// exact GELU, 0.5 x (1 + erf(x / sqrt 2))  (HF/activations.py:70-89 -> torch gelu "none")
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+struct SampleRules {
+  int eos, pad, no_ts, ts_begin, max_initial, vocab;
+};
+
+// ---- GEMM front door (gemm_simt.cu / gemm_tc.cu) ---------------------------------------------------
+enum Epilogue {
+  EPI_STORE = 0,     // out = acc + bias
+  EPI_GELU = 1,      // out = gelu(acc + bias)
+  EPI_RESID = 2,     // out(f32) += acc + bias            (residual stream, in place)
+  EPI_GELU_POS = 3,  // out(f32) = gelu(acc + bias) + pos[row % pos_period]   (conv2 + sinusoid table)
+};
+
+struct GemmArgs {
+  const void* A;      // [M, K] row-major, lda elements between rows
+  const void* W;      // [N, K] row-major (nn.Linear layout)
+  const float* bias;  // [N] or nullptr
+  void* out;          // [M, N] row-major, ldo elements between rows
+  const float* pos;   // EPI_GELU_POS only: [pos_period, N]
+  int M, N, K, lda, ldo, pos_period;
+  int epi;
+  kw_dtype a_type, w_type, out_type;
+};
+
+int gemm_simt(const GemmArgs& g, cudaStream_t st);
+// tcgen05 + TMA path (bf16 A, bf16 W); returns KW_ERR_UNSUPPORTED when the shape does not fit its tiling.
+int gemm_tc(const GemmArgs& g, cudaStream_t st);
+int gemm(const GemmArgs& g, cudaStream_t st);  // dispatch: tensor path when eligible and enabled
+
+}  // namespace kw

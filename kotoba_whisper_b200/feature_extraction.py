@@ -1,0 +1,176 @@
+"""Drop-in for `transformers.WhisperFeatureExtractor` backed by the fused CUDA log-mel kernel.
+
+Mirrors the call surface the reference uses (HF/models/whisper/feature_extraction_whisper.py:189-342; callers:
+run_pseudo_labelling.py:219,268, run_data_filtering.py:338, HF ASR pipeline `chunk_iter`): same constructor arguments,
+same `__call__` keywords, same `input_features` / `attention_mask` outputs, same ValueErrors.  The arithmetic runs in
+`kw_logmel` (csrc/logmel.cu); there is no CPU path — without a CUDA device and libkwb200.so the call raises.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class BatchFeature(dict):
+    """Minimal stand-in for transformers.BatchFeature: a dict with attribute access and `.to()`."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def to(self, *args, **kwargs):
+        return BatchFeature({k: (v.to(*args, **kwargs) if isinstance(v, torch.Tensor) else v) for k, v in self.items()})
+
+
+def _convert(value, return_tensors):
+    if return_tensors is None or return_tensors == "np":
+        return value.cpu().numpy() if isinstance(value, torch.Tensor) else np.asarray(value)
+    if return_tensors == "pt":
+        return value if isinstance(value, torch.Tensor) else torch.from_numpy(np.asarray(value))
+    raise ValueError(f"return_tensors={return_tensors!r} is not supported (use None, 'np' or 'pt')")
+
+
+class WhisperFeatureExtractorB200:
+    model_input_names = ["input_features"]
+
+    def __init__(self, feature_size: int = 80, sampling_rate: int = 16000, hop_length: int = 160, chunk_length: int = 30,
+                 n_fft: int = 400, padding_value: float = 0.0, dither: float = 0.0,
+                 return_attention_mask: bool = False, device: Union[str, torch.device] = "cuda", **kwargs):
+        if n_fft != 400 or hop_length != 160:
+            raise ValueError("the CUDA log-mel kernel implements Whisper's fixed n_fft=400 / hop_length=160 framing")
+        if not 0 < feature_size <= 128 or feature_size % 4:
+            raise ValueError(f"feature_size={feature_size} unsupported (multiple of 4, <= 128)")
+        self.feature_size = feature_size
+        self.sampling_rate = sampling_rate
+        self.hop_length = hop_length
+        self.chunk_length = chunk_length
+        self.n_fft = n_fft
+        self.padding_value = padding_value
+        self.dither = dither
+        self.return_attention_mask = return_attention_mask
+        self.n_samples = chunk_length * sampling_rate
+        self.nb_max_frames = self.n_samples // hop_length
+        self.padding_side = "right"
+        self.device = torch.device(device)
+        self._pinned: Optional[torch.Tensor] = None
+        self._copy_done: Optional[torch.cuda.Event] = None
+
+    # ---- device entry: already-padded clips on the GPU ---------------------------------------------------------
+    def logmel_device(self, audio: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """audio: CUDA f32 [B, n_samples] (zero right-padded or with `lengths`) -> CUDA f32 [B, n_mels, n_samples//160]."""
+        if not audio.is_cuda:
+            raise _lib.KwError("logmel_device needs a CUDA tensor (there is no CPU path)")
+        audio = audio.contiguous().to(torch.float32)
+        B, n = audio.shape
+        out = torch.empty((B, self.feature_size, n // self.hop_length), dtype=torch.float32, device=audio.device)
+        clip_max = torch.empty((B,), dtype=torch.float32, device=audio.device)
+        lens_ptr = None
+        if lengths is not None:
+            lengths = lengths.to(device=audio.device, dtype=torch.int32).contiguous()
+            lens_ptr = lengths.data_ptr()
+        lib = _lib.load()
+        with torch.cuda.device(audio.device):
+            st = torch.cuda.current_stream(audio.device).cuda_stream
+            _lib.check(lib.kw_logmel(audio.data_ptr(), lens_ptr, B, n, self.feature_size, out.data_ptr(),
+                                     clip_max.data_ptr(), st), "kw_logmel")
+        return out
+
+    # ---- reference call surface ------------------------------------------------------------------------------------
+    def __call__(self, raw_speech, truncation: bool = True, pad_to_multiple_of: Optional[int] = None,
+                 return_tensors: Optional[str] = None, return_attention_mask: Optional[bool] = None,
+                 padding: Optional[str] = "max_length", max_length: Optional[int] = None,
+                 sampling_rate: Optional[int] = None, do_normalize: Optional[bool] = None,
+                 device: Optional[str] = None, return_token_timestamps: Optional[bool] = None,
+                 keep_on_device: bool = False, **kwargs) -> BatchFeature:
+        if sampling_rate is not None and sampling_rate != self.sampling_rate:
+            raise ValueError(
+                f"The model corresponding to this feature extractor: {self.__class__.__name__} was trained using a"
+                f" sampling rate of {self.sampling_rate}. Please make sure that the provided `raw_speech` input"
+                f" was sampled with {self.sampling_rate} and not {sampling_rate}.")
+        is_batched_numpy = isinstance(raw_speech, np.ndarray) and raw_speech.ndim > 1
+        if is_batched_numpy and raw_speech.ndim > 2:
+            raise ValueError(f"Only mono-channel audio is supported for input to {self}")
+        is_batched = is_batched_numpy or (isinstance(raw_speech, (list, tuple)) and len(raw_speech) > 0 and
+                                          isinstance(raw_speech[0], (np.ndarray, tuple, list, torch.Tensor)))
+        clips = list(raw_speech) if is_batched else [raw_speech]
+        clips = [c.detach().cpu().numpy() if isinstance(c, torch.Tensor) else np.asarray(c) for c in clips]
+        clips = [c.astype(np.float32, copy=False).reshape(-1) for c in clips]
+
+        lens = [len(c) for c in clips]
+        if padding in ("max_length", True) or padding is None and max_length is not None:
+            target = max_length if max_length else self.n_samples
+        elif padding == "longest":
+            target = max(lens)
+            if max_length is not None and truncation:
+                target = min(target, max_length)
+        elif padding in (False, "do_not_pad", None):
+            if len(set(lens)) != 1:
+                raise ValueError("padding disabled but clips have different lengths")
+            target = lens[0]
+        else:
+            raise ValueError(f"unknown padding strategy {padding!r}")
+        if pad_to_multiple_of:
+            target = -(-target // pad_to_multiple_of) * pad_to_multiple_of
+        if any(l > target for l in lens) and not truncation:
+            raise ValueError("clip longer than max_length with truncation=False")
+        if target < self.n_fft:
+            raise ValueError(f"padded length {target} is shorter than one STFT window ({self.n_fft})")
+        lens = [min(l, target) for l in lens]
+        B = len(clips)
+
+        # stage through one pinned buffer -> one H2D copy
+        if self._pinned is None or self._pinned.numel() < B * target:
+            self._pinned = torch.empty(B * target, dtype=torch.float32).pin_memory()
+        if self._copy_done is not None:
+            self._copy_done.synchronize()  # the previous call's async H2D copy has drained the staging buffer
+        host = self._pinned[: B * target].view(B, target)
+        host_np = host.numpy()
+        for i, c in enumerate(clips):
+            host_np[i, : lens[i]] = c[: lens[i]]
+            host_np[i, lens[i]:] = self.padding_value
+        dev = self.device if device in (None, "cpu") else torch.device(device)
+        audio = host.to(dev, non_blocking=True)
+        self._copy_done = torch.cuda.Event()
+        self._copy_done.record(torch.cuda.current_stream(dev))
+        lens_t = torch.tensor(lens, dtype=torch.int32)
+        if do_normalize:  # zero-mean / unit-variance over the valid samples (feature_extraction_whisper.py:166-187)
+            mask = torch.arange(target, device=dev)[None, :] < lens_t.to(dev)[:, None]
+            cnt = lens_t.to(dev).clamp(min=1).to(torch.float32)[:, None]
+            mean = (audio * mask).sum(1, keepdim=True) / cnt
+            var = (((audio - mean) * mask) ** 2).sum(1, keepdim=True) / cnt
+            audio = torch.where(mask, (audio - mean) / torch.sqrt(var + 1e-7), torch.full_like(audio, self.padding_value))
+        if self.dither != 0.0:
+            audio = audio + self.dither * torch.randn_like(audio)
+        feats = self.logmel_device(audio)
+
+        out = BatchFeature()
+        out["input_features"] = feats if keep_on_device else feats.cpu()
+        if return_attention_mask or (return_attention_mask is None and self.return_attention_mask):
+            m = (np.arange(target)[None, :] < np.asarray(lens)[:, None]).astype(np.int32)[:, :: self.hop_length]
+            if target % self.hop_length != 0:
+                m = m[:, :-1]
+            out["attention_mask"] = torch.from_numpy(np.ascontiguousarray(m))
+        if keep_on_device:
+            if return_tensors not in (None, "pt"):
+                raise ValueError("keep_on_device=True returns torch tensors")
+            return out
+        return BatchFeature({k: _convert(v, return_tensors) for k, v in out.items()})
+
+    def pad(self, processed_features, padding="longest", max_length=None, truncation=False, pad_to_multiple_of=None,
+            return_attention_mask=None, return_tensors=None) -> BatchFeature:
+        """Collate already-extracted features, as DataCollatorSpeechSeq2SeqWithPadding does
+        (run_pseudo_labelling.py:154-158): list of {"input_features": [n_mels, T]} -> {"input_features": [B, n_mels, T]}."""
+        if isinstance(processed_features, (list, tuple)):
+            feats = [np.asarray(f["input_features"], dtype=np.float32) for f in processed_features]
+        else:
+            feats = [np.asarray(f, dtype=np.float32) for f in processed_features["input_features"]]
+        T = max(f.shape[-1] for f in feats)
+        if any(f.shape[-1] != T for f in feats):
+            feats = [np.pad(f, ((0, 0), (0, T - f.shape[-1])), constant_values=self.padding_value) for f in feats]
+        return BatchFeature({"input_features": _convert(np.stack(feats, 0), return_tensors)})

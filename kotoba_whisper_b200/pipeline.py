@@ -1,0 +1,105 @@
+"""Chunked long-form transcription as `run_speed_eval.py` / `run_short_form_eval.py` drive it through the HF ASR
+pipeline: 15 s windows with a 2.5 s stride on each side, every window padded to 30 s, one greedy
+`generate` per batch of windows (no timestamps), then a token-level longest-common-sequence merge of neighbouring windows.
+
+Restates HF/pipelines/automatic_speech_recognition.py:61-84 (`chunk_iter`), :428-444 (chunk / stride sizes) and
+HF/models/whisper/tokenization_whisper.py:1153-1270 (`_find_longest_common_sequence`).  The merge works on token ids, so
+no tokenizer is needed; special ids (>= eos) are dropped before merging, as `_decode_asr` does for text-only output.
+"""
+from __future__ import annotations
+
+from typing import Iterator, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+
+def chunk_spans(n_samples: int, chunk_len: int, stride_left: int, stride_right: int):
+    """Yield (start, end, (chunk_len, left, right), is_last) exactly as the pipeline's chunk_iter walks the audio."""
+    step = chunk_len - stride_left - stride_right
+    if step <= 0:
+        raise ValueError("chunk_len must exceed stride_left + stride_right")
+    for start in range(0, n_samples, step):
+        end = min(start + chunk_len, n_samples)
+        is_last = start + chunk_len >= n_samples
+        left = 0 if start == 0 else stride_left
+        right = 0 if is_last else stride_right
+        if end - start > left:
+            yield start, end, (end - start, left, right), is_last
+        if is_last:
+            break
+
+
+def chunk_iter(inputs: np.ndarray, feature_extractor, chunk_len: int, stride_left: int, stride_right: int,
+               dtype=None) -> Iterator[dict]:
+    """Same contract as the HF pipeline helper: one dict per window with `input_features`, `attention_mask`, `stride`."""
+    for start, end, stride, is_last in chunk_spans(inputs.shape[0], chunk_len, stride_left, stride_right):
+        processed = feature_extractor(inputs[start:end], sampling_rate=feature_extractor.sampling_rate,
+                                      return_tensors="pt", return_attention_mask=True)
+        if dtype is not None:
+            processed = processed.to(dtype=dtype)
+        yield {"is_last": is_last, "stride": stride, **processed}
+
+
+def _merge_pair_indices(left: Sequence[int], right: Sequence[int]):
+    """Best sliding overlap between the tail of `left` and the head of `right` (fraction of equal tokens, > 1 match,
+    longer overlaps favoured by i/10000) -> (left_start, left_stop, right_start, right_stop)."""
+    ll, rl = len(left), len(right)
+    la, ra = np.asarray(left, dtype=np.int64), np.asarray(right, dtype=np.int64)
+    best, best_idx = 0.0, (ll, ll, 0, 0)
+    for i in range(1, ll + rl):
+        l0, l1 = max(0, ll - i), min(ll, ll + rl - i)
+        r0, r1 = max(0, i - ll), min(rl, i)
+        matches = int(np.sum(la[l0:l1] == ra[r0:r1]))
+        score = matches / i + i / 10000.0
+        if matches > 1 and score > best:
+            best, best_idx = score, (l0, l1, r0, r1)
+    return best_idx
+
+
+def merge_chunk_tokens(sequences: Sequence[Sequence[int]]) -> List[int]:
+    """Token-level merge of consecutive windows: keep the left window up to the middle of the matched overlap and the
+    right window from the middle on (left half trusted to the left window, right half to the right one)."""
+    if not sequences:
+        return []
+    left = list(sequences[0])
+    total: List[int] = []
+    for right in sequences[1:]:
+        right = list(right)
+        l0, l1, r0, r1 = _merge_pair_indices(left, right)
+        total.extend(left[: (l0 + l1) // 2])
+        left = right[(r0 + r1) // 2:]
+    total.extend(left)
+    return total
+
+
+def transcribe_longform(model, feature_extractor, audio: np.ndarray, chunk_length_s: float = 15.0,
+                        stride_length_s: Optional[float] = None, batch_size: int = 64, language: Optional[str] = None,
+                        task: Optional[str] = None, max_new_tokens: Optional[int] = None,
+                        return_chunk_tokens: bool = False):
+    """audio: mono float waveform at feature_extractor.sampling_rate -> merged text token ids (list of int).
+
+    Window sizes follow the pipeline: chunk_len = round(chunk_length_s * sr), stride = chunk_length_s / 6 on each side.
+    All windows are featurised by one batched log-mel launch per `batch_size` windows and decoded greedily without
+    timestamps; `num_beams` is 1 as in the transformers version the reference was written against."""
+    sr = feature_extractor.sampling_rate
+    audio = np.asarray(audio, dtype=np.float32).reshape(-1)
+    chunk_len = int(round(chunk_length_s * sr))
+    stride_s = chunk_length_s / 6 if stride_length_s is None else stride_length_s
+    stride = int(round(stride_s * sr))
+    spans = list(chunk_spans(audio.shape[0], chunk_len, stride, stride))
+    eos = model.generation_config.eos_token_id
+    per_chunk: List[List[int]] = []
+    for b0 in range(0, len(spans), batch_size):
+        batch = spans[b0:b0 + batch_size]
+        feats = feature_extractor([audio[s:e] for s, e, _, _ in batch], sampling_rate=sr, return_tensors="pt",
+                                  keep_on_device=True)["input_features"]
+        kw = {} if max_new_tokens is None else {"max_new_tokens": max_new_tokens}
+        ids = model.generate(feats, language=language, task=task, return_timestamps=False, **kw)
+        ids = ids.cpu().tolist()
+        for row in ids:
+            per_chunk.append([t for t in row if t < eos])
+    merged = merge_chunk_tokens([c for c in per_chunk if c])
+    if return_chunk_tokens:
+        return merged, per_chunk, [s[2] for s in spans]
+    return merged

@@ -1,0 +1,103 @@
+"""Generate the golden fixtures under tests/golden/ by running the REFERENCE implementation
+(transformers' Whisper — the code the reference repo calls at run_pseudo_labelling.py:268,338) on CPU fp32.
+
+    python tests/golden/make_golden.py [logmel] [tiny] [kotoba] [teacher]
+
+Inputs are seeded synthetic audio (tests/_synth.py) and random-init weights (torch.manual_seed(0), tests/_hf.py), so
+every consumer can rebuild bit-identical inputs; only the (small) outputs are committed.  Run in the build container;
+the fixtures travel to the GPU box with the repo.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from _hf import build_hf  # noqa: E402
+from _synth import KOTOBA, TEACHER, TINY, TINY80, clips  # noqa: E402
+from oracle.logmel_ref import logmel_batch_f64, pad_or_trim  # noqa: E402
+
+
+def golden_logmel():
+    from transformers import WhisperFeatureExtractor
+    out = {}
+    for nm in (80, 128):
+        fe = WhisperFeatureExtractor(feature_size=nm)
+        cl = clips("UGSS", 500 + nm)
+        cl.append(np.zeros(1000, np.float32))  # all-silence clip: every value is the -1.5 floor
+        ht = fe(cl, sampling_rate=16000, return_tensors="np", return_attention_mask=True)
+        hn = fe._np_extract_fbank_features(np.stack([pad_or_trim(c, 480000) for c in cl]), "cpu")
+        # keep every 37th frame (82 of 3000) of every mel row + the full first/last 8 frames
+        out[f"hf_torch_{nm}"] = ht.input_features[:, :, ::37].astype(np.float32)
+        out[f"hf_numpy_{nm}"] = hn[:, :, ::37].astype(np.float32)
+        out[f"hf_numpy_head_{nm}"] = hn[:, :, :8].astype(np.float32)
+        out[f"hf_numpy_tail_{nm}"] = hn[:, :, -8:].astype(np.float32)
+        out[f"mask_sum_{nm}"] = ht.attention_mask.sum(-1).astype(np.int64)
+        out[f"clip_len_{nm}"] = np.array([len(c) for c in cl], np.int64)
+        out[f"hf_numpy_rowsum_{nm}"] = hn.astype(np.float64).sum(-1)  # [B, n_mels] checksum over all frames
+    np.savez_compressed(os.path.join(HERE, "logmel.npz"), **out)
+    print("logmel.npz written")
+
+
+def _gen_cases(model, mel, tag, out, cases):
+    with torch.no_grad():
+        enc = model.model.encoder(mel).last_hidden_state
+        out[f"{tag}_enc_sub"] = enc[:, ::97, ::5].numpy().astype(np.float32)
+        out[f"{tag}_enc_absmean"] = enc.abs().mean(dim=(1, 2)).numpy()
+        for ts, ml, lang, task in cases:
+            t0 = time.time()
+            ids = model.generate(mel, language=lang, task=task, return_timestamps=ts, max_length=ml, num_beams=1)
+            key = f"{tag}_ids_ts{int(ts)}_ml{ml}_{lang}_{task}"
+            out[key] = ids.numpy().astype(np.int64)
+            print(key, tuple(ids.shape), f"{time.time() - t0:.1f}s", flush=True)
+        # raw logits + top-2 margins of the no-timestamp greedy run (triage data for near-ties)
+        r = model.generate(mel, language="ja", task="transcribe", return_timestamps=False, max_length=cases[0][1],
+                           num_beams=1, return_dict_in_generate=True, output_scores=True, output_logits=True)
+        sc = torch.stack(r.scores)  # [steps, B, V] processed
+        top2 = sc.topk(2, dim=-1).values
+        out[f"{tag}_margins_ts0"] = (top2[..., 0] - top2[..., 1]).numpy().astype(np.float32)
+        lg = torch.stack(r.logits)
+        out[f"{tag}_logits0_sub"] = lg[0][:, ::53].numpy().astype(np.float32)  # first-step raw logits, every 53rd
+
+
+def golden_tiny():
+    out = {}
+    for name, arch in (("tiny", TINY), ("tiny80", TINY80)):
+        model = build_hf(arch)
+        mel = torch.from_numpy(logmel_batch_f64(clips("UGS", 7), arch["num_mel_bins"]))
+        _gen_cases(model, mel, name, out,
+                   [(True, 40, "ja", "transcribe"), (True, 128, "ja", "transcribe"), (False, 40, "ja", "transcribe"),
+                    (False, 128, "ja", "transcribe"), (True, 64, "en", "translate")])
+    np.savez_compressed(os.path.join(HERE, "tiny.npz"), **out)
+    print("tiny.npz written")
+
+
+def golden_full(name, arch, spec, seed0, cases):
+    out = {}
+    t0 = time.time()
+    model = build_hf(arch)
+    print(name, "built", f"{time.time() - t0:.1f}s", flush=True)
+    mel = torch.from_numpy(logmel_batch_f64(clips(spec, seed0), arch["num_mel_bins"]))
+    _gen_cases(model, mel, name, out, cases)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
+    print(f"{name}.npz written", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["logmel", "tiny", "kotoba"]
+    torch.set_num_threads(os.cpu_count())
+    if "logmel" in what:
+        golden_logmel()
+    if "tiny" in what:
+        golden_tiny()
+    if "kotoba" in what:  # BASELINE.json configs[0]: batch 4 x 30 s, ja/transcribe, timestamps, max_length 128
+        golden_full("kotoba", KOTOBA, "UGSG", 1000, [(True, 128, "ja", "transcribe"), (False, 128, "ja", "transcribe")])
+    if "teacher" in what:  # configs[2] architecture at a CPU-runnable batch of 2
+        golden_full("teacher", TEACHER, "GS", 3000, [(True, 128, "ja", "transcribe")])
