@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the transcription hot path (BASELINE.json metric: RTFx = input audio-seconds per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[1] — kotoba-whisper-v2.0 architecture (32 enc / 2 dec, d=1280,
+128 mels, random init), bf16, greedy short-form (`return_timestamps=False`, ja/transcribe, max_length 128), batch
+64 x 30 s synthetic 16 kHz audio per GPU.  One step = log-mel -> encoder -> greedy generate over one batch, plus the
+token-id gather across ranks.  `value` times it with the audio already resident in HBM; `e2e` times the public API
+(WhisperFeatureExtractorB200.__call__ + model.generate) from host numpy clips to host token ids, copies included.
+
+N > 1: launched by torchrun, one rank per GPU; every rank transcribes its own batch of 64 clips (weak scaling); the
+only collective is the all_gather of token ids.  `--impl reference` times the reference's own implementation of the
+path (transformers fp32 generate on the host CPU) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+KOTOBA = dict(vocab_size=51866, num_mel_bins=128, d_model=1280, encoder_layers=32, decoder_layers=2,
+              encoder_attention_heads=20, decoder_attention_heads=20, encoder_ffn_dim=5120, decoder_ffn_dim=5120)
+BATCH = 64
+MAX_LENGTH = 128
+SR = 16000
+CLIP_S = 30
+WORKLOAD = "kotoba-whisper-v2.0 arch (32enc/2dec d1280 128mel, random init) greedy short-form ja/transcribe " \
+           "max_length 128, batch 64 x 30 s synthetic 16 kHz audio per GPU"
+
+
+def synth_audio(batch: int, seed: int) -> np.ndarray:
+    """The reference's own dummy-audio recipe (run_speed_eval.py:14-17) for half the clips, gaussian for the rest."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((batch, SR * CLIP_S), np.float32)
+    for i in range(batch):
+        if i % 2 == 0:
+            out[i] = (rng.random(SR * CLIP_S, dtype=np.float32) - 0.5) * 2 * 0.007
+        else:
+            out[i] = rng.standard_normal(SR * CLIP_S, dtype=np.float32) * 0.1
+    return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1400.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def reference_arm(args, rank: int, world: int):
+    """transformers fp32 greedy generate on the host CPU — the reference's own code path (run_pseudo_labelling.py:268,338
+    with the feature extractor's torch STFT) — on a bounded sample: `ref_batch` clips of the same workload per step."""
+    if rank != 0:
+        return
+    from transformers import WhisperFeatureExtractor
+    from _hf import build_hf
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = build_hf(KOTOBA, seed=0, dtype=torch.float32)
+    fe = WhisperFeatureExtractor(feature_size=128)
+    nb = args.ref_batch
+    audio = synth_audio(nb, seed=1000)
+
+    def step():
+        feats = fe(list(audio), sampling_rate=SR, return_tensors="pt").input_features
+        with torch.no_grad():
+            return model.generate(feats, language="ja", task="transcribe", return_timestamps=False,
+                                  max_length=MAX_LENGTH, num_beams=1)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    rtfx = nb * CLIP_S * args.steps / dt
+    sample = f"{nb} of the {BATCH} clips per step (same arch, fp32, CPU), {args.steps} steps"
+    line = {"impl": "reference", "metric": "RTFx", "value": rtfx, "unit": "audio_s/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "reference_sample": sample},
+            "cpu_baseline": {"value": rtfx, "unit": "audio_s/s", "cores": threads, "kind": "reference",
+                             "sample": sample},
+            "e2e": {"value": rtfx, "unit": "audio_s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(clips: int = 1):
+    """Bounded CPU sample for the `cpu_baseline` object of our own line: HF fp32 on `clips` clips, one timed pass."""
+    from transformers import WhisperFeatureExtractor
+    from _hf import build_hf
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    model = build_hf(KOTOBA, seed=0, dtype=torch.float32)
+    fe = WhisperFeatureExtractor(feature_size=128)
+    audio = synth_audio(clips, seed=1000)
+    t0 = time.perf_counter()
+    feats = fe(list(audio), sampling_rate=SR, return_tensors="pt").input_features
+    with torch.no_grad():
+        model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=MAX_LENGTH, num_beams=1)
+    dt = time.perf_counter() - t0
+    return {"value": clips * CLIP_S / dt, "unit": "audio_s/s", "cores": threads, "kind": "reference",
+            "sample": f"{clips} clip(s) x 30 s of the same workload through transformers fp32 generate, one pass "
+                      f"({dt:.1f} s)"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def ours(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+    from kotoba_whisper_b200 import (WhisperB200Config, WhisperB200ForConditionalGeneration,
+                                     WhisperFeatureExtractorB200, _lib)
+    from kotoba_whisper_b200.distributed import gather_token_ids
+    from kotoba_whisper_b200.random_init import random_state_dict
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    cfg = WhisperB200Config(**KOTOBA)
+    sd = random_state_dict(cfg, seed=0, device=dev)
+    model = WhisperB200ForConditionalGeneration.from_state_dict(sd, cfg, dtype=torch.bfloat16, max_batch=BATCH, device=dev)
+    del sd
+    torch.cuda.empty_cache()
+    fe = WhisperFeatureExtractorB200(feature_size=128, device=dev)
+    audio_host = synth_audio(BATCH, seed=1000 * 1 + rank)       # seed = 1000*config + rank
+    audio_dev = torch.from_numpy(audio_host).to(dev)
+    clips_host = list(audio_host)
+    pad = model.generation_config.pad_token_id
+    stats = {}
+
+    def step_resident():
+        feats = fe.logmel_device(audio_dev)
+        ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=MAX_LENGTH,
+                             stats=stats)
+        return gather_token_ids(ids, pad)
+
+    def step_e2e():
+        feats = fe(clips_host, sampling_rate=SR, return_tensors="pt", keep_on_device=True)["input_features"]
+        ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=MAX_LENGTH)
+        ids = gather_token_ids(ids, pad)
+        return ids.cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    for _ in range(args.warmup):
+        step_resident()
+    prof_mask = (1 << _lib.PROF_ENC_GEMM) | (1 << _lib.PROF_ENC_ATTN) | (1 << _lib.PROF_DEC_CROSS) | (1 << _lib.PROF_LOGMEL)
+    for c in range(6):
+        _lib.profile_read(c, reset=True)
+    lib.kw_profile_enable(prof_mask)
+    lib.kw_launch_count(1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, ids = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = int(lib.kw_launch_count(0))
+    prof = {c: _lib.profile_read(c, reset=True) for c in (_lib.PROF_ENC_GEMM, _lib.PROF_ENC_ATTN, _lib.PROF_DEC_CROSS,
+                                                          _lib.PROF_LOGMEL)}
+    lib.kw_profile_enable(0)
+    passes = stats.get("passes", 0)
+
+    step_e2e()
+    ms_e2e, ids_host = timed(step_e2e, args.steps)
+
+    audio_s = BATCH * CLIP_S * world
+    value = audio_s * args.steps / (ms / 1e3)
+    e2e = audio_s * args.steps / (ms_e2e / 1e3)
+    if rank != 0:
+        return
+    hbm, tf_sus, tf_burst, peak_src = load_peaks()
+
+    def leg(cat, unit_scale):
+        t, n, work = prof[cat]
+        return (work / unit_scale) / (t / 1e3) if t > 0 else 0.0, n, t
+
+    g_tf, g_n, g_ms = leg(_lib.PROF_ENC_GEMM, 1e12)
+    a_tf, a_n, a_ms = leg(_lib.PROF_ENC_ATTN, 1e12)
+    x_gb, x_n, x_ms = leg(_lib.PROF_DEC_CROSS, 1e9)
+    m_gb, m_n, m_ms = leg(_lib.PROF_LOGMEL, 1e9)
+    roofline = {"kernel": "encoder GEMMs (conv stem, QKV, out, fc1, fc2)", "bound": "tensor", "achieved": g_tf,
+                "peak": tf_sus, "unit": "TFLOP/s", "frac": g_tf / tf_sus, "traffic": None, "peak_source": peak_src,
+                "launches": g_n, "share_of_step": g_ms / ms}
+    extra = [
+        {"kernel": "encoder self-attention", "bound": "tensor", "achieved": a_tf, "peak": tf_sus, "unit": "TFLOP/s",
+         "frac": a_tf / tf_sus, "launches": a_n, "share_of_step": a_ms / ms},
+        {"kernel": "decode-step cross-attention", "bound": "hbm", "achieved": x_gb, "peak": hbm, "unit": "GB/s",
+         "frac": x_gb / hbm, "launches": x_n, "share_of_step": x_ms / ms},
+        {"kernel": "log-mel (stft+mel+log, incl. fix-up pass)", "bound": "hbm", "achieved": m_gb, "peak": hbm,
+         "unit": "GB/s", "frac": m_gb / hbm, "launches": m_n, "share_of_step": m_ms / ms},
+    ]
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline_leg(1)
+        except Exception as e:  # the CPU leg is a reported baseline, never a reason to lose the GPU number
+            cpu = {"value": None, "unit": "audio_s/s", "cores": os.cpu_count(), "kind": "reference",
+                   "sample": f"failed: {type(e).__name__}: {e}"}
+    line = {"metric": "RTFx", "value": value, "unit": "audio_s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
+                       "passes_per_step": passes, "l2": "inputs_larger_than_l2 (123 MB audio + 1.5 GB weights per step)",
+                       "tokens_out_shape": list(ids.shape)},
+            "roofline": roofline, "roofline_extra": extra, "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": "audio_s/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(audio_host.nbytes) * world,
+                    "d2h_bytes_per_step": int(ids_host.numel() * ids_host.element_size())},
+            "gpu_launches": launches, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=1, help="clips per step of the bounded CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -184,6 +184,22 @@ int kw_layernorm(const float* x, const float* w, const float* b, void* out, int3
 int kw_sample(kw_model* m, const float* logits, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos,
               int32_t begin_index, int32_t return_timestamps, int32_t* finished, kw_stream stream);
 
+/* ---- optional device timing of kernel categories (CUDA events on the launching stream) ---------------------------
+ * kw_profile_enable(mask) turns on event pairs around every launch of the categories in `mask` (bit = category);
+ * kw_profile_read returns the summed device time, launch count and ALGORITHMIC work (FLOPs for GEMM / attention
+ * categories, bytes for the memory-bound ones) since the last reset; it synchronises on the recorded events. */
+enum {
+  KW_PROF_ENC_GEMM = 0,  /* conv-stem, QKV, out, fc1, fc2 projections of kw_encode (FLOPs) */
+  KW_PROF_ENC_ATTN = 1,  /* encoder self-attention (FLOPs: 4 B H S S 64) */
+  KW_PROF_XKV_GEMM = 2,  /* one-shot cross K/V projection (FLOPs) */
+  KW_PROF_DEC_GEMM = 3,  /* decode-step projections incl. vocab (FLOPs) */
+  KW_PROF_DEC_CROSS = 4, /* decode-step cross-attention (bytes: cached K and V read once) */
+  KW_PROF_LOGMEL = 5,    /* log-mel (bytes: audio in + features out) */
+  KW_PROF_NCAT = 6
+};
+void kw_profile_enable(uint32_t category_mask);
+int kw_profile_read(int32_t category, double* total_ms, int64_t* launches, double* work, int32_t reset);
+
 /* 0: auto (tcgen05 where eligible), 1: force SIMT GEMMs, 2: force tcgen05 (error if ineligible). Process-wide. */
 void kw_set_gemm_impl(int32_t impl);
 /* counts kernels launched by this library since the last reset (bench.py's gpu_launches) */

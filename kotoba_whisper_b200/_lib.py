@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkwb200.so")
 
 KW_F32, KW_BF16 = 0, 1
+PROF_ENC_GEMM, PROF_ENC_ATTN, PROF_XKV_GEMM, PROF_DEC_GEMM, PROF_DEC_CROSS, PROF_LOGMEL = range(6)
 vp, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
 
 
@@ -61,6 +62,8 @@ SIGNATURES = {
     "kw_sample": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "kw_set_gemm_impl": (None, [i32]),
     "kw_launch_count": (i64, [i32]),
+    "kw_profile_enable": (None, [C.c_uint32]),
+    "kw_profile_read": (i32, [i32, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double), i32]),
 }
 
 _lib = None
@@ -79,6 +82,13 @@ def load() -> C.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib
+
+
+def profile_read(category: int, reset: bool = True):
+    """-> (device ms, launches, algorithmic work) of one kernel category since the last reset."""
+    ms, n, work = C.c_double(), i64(), C.c_double()
+    check(load().kw_profile_read(category, C.byref(ms), C.byref(n), C.byref(work), int(reset)), "kw_profile_read")
+    return ms.value, n.value, work.value
 
 
 def check(rc: int, what: str = "") -> int:

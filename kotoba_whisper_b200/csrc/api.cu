@@ -58,6 +58,49 @@ int gemm(const GemmArgs& g, cudaStream_t st) {
 
 static size_t esize(kw_dtype t) { return t == KW_BF16 ? 2 : 4; }
 
+// ---- optional per-category device timing (CUDA events on the launching stream; bench.py's roofline legs) -----------
+struct ProfRec {
+  int cat;
+  cudaEvent_t a, b;
+};
+struct Profiler {
+  unsigned mask = 0;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  double work[KW_PROF_NCAT] = {0};
+  long long count[KW_PROF_NCAT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+static Profiler g_prof;
+
+struct ProfScope {
+  int cat;
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  ProfScope(int cat_, double work, cudaStream_t st_) : cat(cat_), st(st_) {
+    if (!(g_prof.mask & (1u << cat))) return;
+    cudaEvent_t a = g_prof.get();
+    b = g_prof.get();
+    cudaEventRecord(a, st);
+    g_prof.recs.push_back({cat, a, b});
+    g_prof.work[cat] += work;
+    g_prof.count[cat] += 1;
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, st);
+  }
+};
+static double gemm_flops(const GemmArgs& g) { return 2.0 * g.M * (double)g.N * g.K; }
+
 }  // namespace kw
 
 using namespace kw;
@@ -91,6 +134,38 @@ extern "C" {
 const char* kw_last_error(void) { return g_err; }
 const char* kw_version(void) { return "kwb200 0.1 (sm_100a)"; }
 void kw_set_gemm_impl(int32_t impl) { g_gemm_impl.store(impl); }
+
+void kw_profile_enable(uint32_t category_mask) { g_prof.mask = category_mask; }
+
+int kw_profile_read(int32_t category, double* total_ms, int64_t* launches, double* work, int32_t reset) {
+  KW_REQUIRE(category >= 0 && category < KW_PROF_NCAT, "kw_profile_read: bad category %d", category);
+  double ms = 0.0;
+  for (auto& r : g_prof.recs) {
+    if (r.cat != category) continue;
+    float t = 0.0f;
+    KW_CUDA_OK(cudaEventSynchronize(r.b));
+    KW_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = g_prof.count[category];
+  if (work) *work = g_prof.work[category];
+  if (reset) {
+    std::vector<ProfRec> keep;
+    for (auto& r : g_prof.recs) {
+      if (r.cat == category) {
+        g_prof.pool.push_back(r.a);
+        g_prof.pool.push_back(r.b);
+      } else {
+        keep.push_back(r);
+      }
+    }
+    g_prof.recs.swap(keep);
+    g_prof.work[category] = 0;
+    g_prof.count[category] = 0;
+  }
+  return KW_OK;
+}
 int64_t kw_launch_count(int32_t reset) {
   long long v = g_launches.load();
   if (reset) g_launches.store(0);
@@ -100,6 +175,7 @@ int64_t kw_launch_count(int32_t reset) {
 int kw_logmel(const float* audio, const int32_t* lens, int32_t B, int32_t n_samples, int32_t n_mels, float* out,
               float* clip_max, kw_stream stream) {
   KW_REQUIRE(audio && out && clip_max, "kw_logmel: null pointer");
+  ProfScope ps(KW_PROF_LOGMEL, (double)B * (4.0 * n_samples + 4.0 * n_mels * (n_samples / 160)), (cudaStream_t)stream);
   return logmel_launch(audio, lens, B, n_samples, n_mels, out, clip_max, (cudaStream_t)stream);
 }
 
@@ -201,6 +277,11 @@ static GemmArgs mk(const void* A, int lda, kw_dtype at, const void* W, kw_dtype 
     if (_rc != KW_OK) return _rc; \
   } while (0)
 
+static int gemm_p(int cat, const GemmArgs& g, cudaStream_t st) {
+  ProfScope ps(cat, gemm_flops(g), st);
+  return gemm(g, st);
+}
+
 int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_stream stream) {
   KW_REQUIRE(m && mel, "kw_encode: null argument");
   KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch, "kw_encode: B=%d outside [1, max_batch=%d]", B, m->cfg.max_batch);
@@ -210,21 +291,22 @@ int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_strea
   const int d = c.d_model, S = c.max_source_pos, T2 = 2 * S, F = c.ffn_dim, M = B * S;
   // conv stem as two im2col GEMMs (modeling_whisper.py:619-625)
   KW_TRY(im2col_conv1(mel, m->bufP, B, c.n_mels, T2, t, st));
-  KW_TRY(gemm(mk(m->bufP, 3 * c.n_mels, t, m->w.conv1_w, t, m->w.conv1_b, m->bufQ, d, t, B * T2, d, 3 * c.n_mels, EPI_GELU), st));
+  KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->bufP, 3 * c.n_mels, t, m->w.conv1_w, t, m->w.conv1_b, m->bufQ, d, t, B * T2, d, 3 * c.n_mels, EPI_GELU), st));
   KW_TRY(im2col_conv2(m->bufQ, m->bufP, B, d, T2, S, t, st));
   {
     GemmArgs g = mk(m->bufP, 3 * d, t, m->w.conv2_w, t, m->w.conv2_b, m->x, d, KW_F32, M, d, 3 * d, EPI_GELU_POS);
     g.pos = m->w.enc_pos;
     g.pos_period = S;
-    KW_TRY(gemm(g, st));
+    KW_TRY(gemm_p(KW_PROF_ENC_GEMM, g, st));
   }
   for (int l = 0; l < c.enc_layers; ++l) {
     const kw_enc_layer_weights& w = m->enc[l];
     KW_TRY(layernorm(m->x, w.ln1_w, w.ln1_b, m->a, M, d, t, st));
-    KW_TRY(gemm(mk(m->a, d, t, w.wqkv, t, w.bqkv, m->bufP, 3 * d, t, M, 3 * d, d, EPI_STORE), st));
+    KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->a, d, t, w.wqkv, t, w.bqkv, m->bufP, 3 * d, t, M, 3 * d, d, EPI_STORE), st));
     {
       const char* qkv = (const char*)m->bufP;
       const size_t es = esize(t);
+      ProfScope ps(KW_PROF_ENC_ATTN, 4.0 * B * c.n_heads * (double)S * S * 64, st);
       int rc = KW_ERR_UNSUPPORTED;
       if (t == KW_BF16 && g_gemm_impl.load() != 1)
         rc = attention_tc(qkv, qkv + d * es, qkv + 2 * d * es, m->o, B, c.n_heads, S, S, (long long)S * 3 * d, 3 * d,
@@ -234,10 +316,10 @@ int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_strea
                             (long long)S * 3 * d, 3 * d, (long long)S * d, d, t, st);
       KW_TRY(rc);
     }
-    KW_TRY(gemm(mk(m->o, d, t, w.wo, t, w.bo, m->x, d, KW_F32, M, d, d, EPI_RESID), st));
+    KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->o, d, t, w.wo, t, w.bo, m->x, d, KW_F32, M, d, d, EPI_RESID), st));
     KW_TRY(layernorm(m->x, w.ln2_w, w.ln2_b, m->a, M, d, t, st));
-    KW_TRY(gemm(mk(m->a, d, t, w.w1, t, w.b1, m->bufQ, F, t, M, F, d, EPI_GELU), st));
-    KW_TRY(gemm(mk(m->bufQ, F, t, w.w2, t, w.b2, m->x, d, KW_F32, M, d, F, EPI_RESID), st));
+    KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->a, d, t, w.w1, t, w.b1, m->bufQ, F, t, M, F, d, EPI_GELU), st));
+    KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->bufQ, F, t, w.w2, t, w.b2, m->x, d, KW_F32, M, d, F, EPI_RESID), st));
   }
   KW_TRY(layernorm(m->x, m->w.enc_ln_w, m->w.enc_ln_b, m->enc_out, M, d, t, st));
   if (enc_out) KW_TRY(layernorm(m->x, m->w.enc_ln_w, m->w.enc_ln_b, enc_out, M, d, KW_F32, st));
@@ -259,7 +341,7 @@ int kw_cross_kv(kw_model* m, int32_t B, kw_stream stream) {
   const size_t layer_stride = (size_t)c.max_batch * S * 2 * d * esize(m->t);
   for (int l = 0; l < c.dec_layers; ++l) {
     const kw_dec_layer_weights& w = m->dec[l];
-    KW_TRY(gemm(mk(m->enc_out, d, m->t, w.wkv_x, m->t, w.bkv_x, (char*)m->xkv + l * layer_stride, 2 * d, m->t, B * S, 2 * d,
+    KW_TRY(gemm_p(KW_PROF_XKV_GEMM, mk(m->enc_out, d, m->t, w.wkv_x, m->t, w.bkv_x, (char*)m->xkv + l * layer_stride, 2 * d, m->t, B * S, 2 * d,
                    d, EPI_STORE), (cudaStream_t)stream));
   }
   return KW_OK;
@@ -275,17 +357,20 @@ static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int 
   for (int l = 0; l < c.dec_layers; ++l) {
     const kw_dec_layer_weights& w = m->dec[l];
     KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, KW_F32, st));
-    KW_TRY(gemm(mk(m->da, d, KW_F32, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, KW_F32, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
     KW_TRY(dec_self_attn(m->dqkv, (char*)m->self_k + l * self_stride, (char*)m->self_v + l * self_stride, m->dattn, B, d,
                          H, MT, pos, t, st));
-    KW_TRY(gemm(mk(m->dattn, d, KW_F32, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, KW_F32, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
     KW_TRY(layernorm(m->dx, w.lnx_w, w.lnx_b, m->da, B, d, KW_F32, st));
-    KW_TRY(gemm(mk(m->da, d, KW_F32, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), st));
-    KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st));
-    KW_TRY(gemm(mk(m->dattn, d, KW_F32, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, KW_F32, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), st));
+    {
+      ProfScope ps(KW_PROF_DEC_CROSS, (double)B * S * 2 * d * esize(t), st);  // algorithmic bytes: K and V read once
+      KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st));
+    }
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, KW_F32, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
     KW_TRY(layernorm(m->dx, w.ln3_w, w.ln3_b, m->da, B, d, KW_F32, st));
-    KW_TRY(gemm(mk(m->da, d, KW_F32, w.w1, t, w.b1, m->dh, F, KW_F32, B, F, d, EPI_GELU), st));
-    KW_TRY(gemm(mk(m->dh, F, KW_F32, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, KW_F32, w.w1, t, w.b1, m->dh, F, KW_F32, B, F, d, EPI_GELU), st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dh, F, KW_F32, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), st));
   }
   return KW_OK;
 }
@@ -301,7 +386,7 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
   if (!sample && !logits_out) return KW_OK;
   KW_TRY(layernorm(m->dx, m->w.dec_ln_w, m->w.dec_ln_b, m->da, B, c.d_model, KW_F32, st));
   float* lg = logits_out ? logits_out : m->logits;
-  KW_TRY(gemm(mk(m->da, c.d_model, KW_F32, m->w.tok_embed, m->t, nullptr, lg, c.vocab_size, KW_F32, B, c.vocab_size,
+  KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, c.d_model, KW_F32, m->w.tok_embed, m->t, nullptr, lg, c.vocab_size, KW_F32, B, c.vocab_size,
                  c.d_model, EPI_STORE), st));
   if (sample) {
     KW_REQUIRE(finished, "kw_decode_step: sample requires the finished array");

@@ -1,10 +1,351 @@
-// tcgen05 / TMA tensor-core kernels (bf16 operands, fp32 accumulation in TMEM).  Placeholder until the kernels land:
-// every entry reports KW_ERR_UNSUPPORTED so the dispatcher takes the SIMT path.
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  out[M,N] = epi(A[M,K] . W[N,K]^T + bias), bf16 operands, fp32 accumulation.
+//
+// Persistent, warp-specialised kernel, one CTA per SM:
+//   warp 4      TMA producer: cp.async.bulk.tensor 2D loads of a 128 x 64 A tile and a 256 x 64 W tile (both K-major,
+//               128-byte swizzle) into a 4-stage shared-memory ring, completion on mbarriers (complete_tx)
+//   warp 5      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) x 4 per stage,
+//               accumulating in TMEM; tcgen05.commit releases the smem stage and, after the last k-block, publishes the
+//               accumulator.  Two 256-column accumulators (all 512 TMEM columns) let tile i+1's MMAs overlap tile i's epilogue
+//   warps 0-3   epilogue: tcgen05.ld 32 lanes x 32 columns at a time -> bias / GELU(erf) / residual / position add in
+//               registers -> direct 16-byte global stores (each thread owns one output row)
+// Tiles are walked n-fastest so the CTAs running together share A row-blocks and the whole weight matrix stays in L2.
+// Every mbarrier wait carries a clock64 watchdog that traps instead of hanging the GPU if a pipeline bug deadlocks.
+#include <cuda.h>
+
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace kw {
 
-int gemm_tc(const GemmArgs&, cudaStream_t) { return KW_ERR_UNSUPPORTED; }
+extern std::atomic<long long> g_launches;
+
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int N_EPI_WARPS = 4, THREADS = 32 * (N_EPI_WARPS + 2);
+constexpr int TMEM_COLS = 512;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+
+struct Params {
+  const float* bias;
+  void* out;
+  const float* pos;
+  int M, N, K, ldo, pos_period, epi, out_bf16;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s: a pipeline bug, not a slow tile
+      printf("kwb200 gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major: 1) | [32,46) SBO >> 4 = 1024 B between 8-row groups
+// | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
+  const int k_blocks = p.K / BK;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), N_EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {  // one warp allocates all 512 TMEM columns (two 256-column accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const uint32_t sa = base + s * STAGE_BYTES;
+          tma_load_2d(sa, &tmA, full_bar(s), kb * BK, m0);
+          tma_load_2d(sa + A_BYTES, &tmB, full_bar(s), kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+        const uint32_t as = tcount & 1;
+        mbar_wait(tempty_bar(as), ((tcount >> 1) & 1) ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar(s), (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint64_t da = make_desc(sa), db = make_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)  // +32 B per K=16 step inside the 128 B swizzle atom
+            umma(d_tmem, da + (uint64_t)(k * UMMA_K * 2 >> 4), db + (uint64_t)(k * UMMA_K * 2 >> 4), (kb | k) != 0);
+          umma_commit(empty_bar(s));  // smem stage reusable once these MMAs have read it
+        }
+        umma_commit(tfull_bar(as));   // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0-3: TMEM lanes 32*warp .. 32*warp+31) =====================
+    uint32_t tcount = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
+      const uint32_t as = tcount & 1;
+      mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < p.M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (p.epi == EPI_GELU || p.epi == EPI_GELU_POS) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          }
+          if (p.epi == EPI_GELU_POS) {
+            const float* pr = p.pos + (size_t)(row % p.pos_period) * p.N + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 q4 = __ldg(reinterpret_cast<const float4*>(pr + j));
+              v[j] += q4.x; v[j + 1] += q4.y; v[j + 2] += q4.z; v[j + 3] += q4.w;
+            }
+          }
+          if (p.out_bf16) {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 w4;
+              w4.x = pack_bf16(v[j], v[j + 1]); w4.y = pack_bf16(v[j + 2], v[j + 3]);
+              w4.z = pack_bf16(v[j + 4], v[j + 5]); w4.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = w4;
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+            if (p.epi == EPI_RESID) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 x4 = *reinterpret_cast<const float4*>(o + j);
+                *reinterpret_cast<float4*>(o + j) = make_float4(x4.x + v[j], x4.y + v[j + 1], x4.z + v[j + 2], x4.w + v[j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tempty_bar(as));  // 128 arrivals hand the accumulator back to the MMA warp
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// 2D bf16 row-major [rows, cols] (ld elements between rows) -> tiles of box_rows x 64 columns, 128 B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled not available from the driver");
+    return KW_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+    return KW_ERR_CUDA;
+  }
+  return KW_OK;
+}
+
+}  // namespace tc
+
+int gemm_tc(const GemmArgs& g, cudaStream_t st) {
+  using namespace tc;
+  if (g.a_type != KW_BF16 || g.w_type != KW_BF16) return KW_ERR_UNSUPPORTED;
+  if (g.K % BK != 0 || g.N % 32 != 0 || g.lda % 8 != 0 || g.ldo % 8 != 0 || g.M < 1) return KW_ERR_UNSUPPORTED;
+  if (((uintptr_t)g.A & 15) || ((uintptr_t)g.W & 15) || ((uintptr_t)g.out & 15)) return KW_ERR_UNSUPPORTED;
+  if ((g.epi == EPI_RESID || g.epi == EPI_GELU_POS) && g.out_type != KW_F32) return KW_ERR_UNSUPPORTED;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, g.A, g.M, g.K, g.lda, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, g.W, g.N, g.K, g.K, BN);
+  if (rc) return rc;
+  static int n_sm = 0;
+  static bool attr = false;
+  if (!attr) {
+    int dev = 0;
+    KW_CUDA_OK(cudaGetDevice(&dev));
+    KW_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    attr = true;
+  }
+  Params p;
+  p.bias = g.bias; p.out = g.out; p.pos = g.pos;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.ldo = g.ldo; p.pos_period = g.pos_period > 0 ? g.pos_period : 1;
+  p.epi = g.epi; p.out_bf16 = g.out_type == KW_BF16;
+  const int n_tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
+  const int grid = std::min(n_tiles, n_sm);
+  gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  KW_LAUNCH_OK();
+  ++g_launches;
+  return KW_OK;
+}
 
 int attention_tc(const void*, const void*, const void*, void*, int, int, int, int, long long, long long, long long,
                  long long, long long, long long, cudaStream_t) {

@@ -57,14 +57,13 @@ def _gen_cases(model, mel, tag, out, cases):
             key = f"{tag}_ids_ts{int(ts)}_ml{ml}_{lang}_{task}"
             out[key] = ids.numpy().astype(np.int64)
             print(key, tuple(ids.shape), f"{time.time() - t0:.1f}s", flush=True)
-        # raw logits + top-2 margins of the no-timestamp greedy run (triage data for near-ties)
-        r = model.generate(mel, language="ja", task="transcribe", return_timestamps=False, max_length=cases[0][1],
-                           num_beams=1, return_dict_in_generate=True, output_scores=True, output_logits=True)
-        sc = torch.stack(r.scores)  # [steps, B, V] processed
-        top2 = sc.topk(2, dim=-1).values
-        out[f"{tag}_margins_ts0"] = (top2[..., 0] - top2[..., 1]).numpy().astype(np.float32)
-        lg = torch.stack(r.logits)
-        out[f"{tag}_logits0_sub"] = lg[0][:, ::53].numpy().astype(np.float32)  # first-step raw logits, every 53rd
+        # raw logits of the first generated position, from a plain forward pass over the 4-token no-timestamp prompt
+        # (generate()'s own `logits` output belongs to the LAST seek pass, which differs when >1 pass ran)
+        prompt = torch.tensor([[50258, 50266, 50360, 50364]] * mel.shape[0])
+        lg = model(input_features=mel, decoder_input_ids=prompt).logits
+        out[f"{tag}_logits0_sub"] = lg[:, -1, ::53].float().numpy().astype(np.float32)
+        top2 = lg[:, -1].float().topk(2, dim=-1).values
+        out[f"{tag}_logits0_margin"] = (top2[:, 0] - top2[:, 1]).numpy().astype(np.float32)
 
 
 def golden_tiny():

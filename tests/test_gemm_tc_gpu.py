@@ -1,0 +1,63 @@
+"""tcgen05 / TMEM / TMA GEMM (kw_linear impl=2) vs torch fp32 on the same bf16 operands, incl. M / N tails and every
+epilogue.  fp32 accumulation: f32 outputs agree to ~1e-5 relative, bf16 outputs to bf16 rounding."""
+import pytest
+import torch
+
+from kotoba_whisper_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+F32, BF16 = _lib.KW_F32, _lib.KW_BF16
+
+
+def _run(A, W, bias, epi, out_dtype, out=None, impl=2):
+    lib = _lib.load()
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.zeros((M, N), dtype=torch.bfloat16 if out_dtype == BF16 else torch.float32, device="cuda")
+    _lib.check(lib.kw_linear(A.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(),
+                             M, N, K, epi, BF16, BF16, out_dtype, impl, torch.cuda.current_stream().cuda_stream), "kw_linear")
+    torch.cuda.synchronize()
+    return out
+
+
+SHAPES = [(128, 256, 64), (256, 512, 128), (100, 128, 128), (1500, 1280, 1280), (6000, 3840, 1280), (6000, 1280, 384),
+          (3000, 1280, 3840), (1500, 5120, 1280), (1500, 1280, 5120), (333, 192, 576), (4 * 1500, 2560, 1280)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tc_matches_torch(M, N, K):
+    torch.manual_seed(M * 7 + N * 3 + K)
+    A = (torch.randn(M, K, device="cuda")).bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(N, device="cuda")
+    ref = torch.nn.functional.linear(A.float(), W.float(), b)
+    scale = max(1.0, ref.abs().max().item())
+    o32 = _run(A, W, b, 0, F32)
+    assert (o32 - ref).abs().max().item() <= 3e-5 * scale, "store f32"
+    o16 = _run(A, W, b, 0, BF16)
+    assert (o16.float() - ref).abs().max().item() <= 1e-2 * scale, "store bf16"
+    g16 = _run(A, W, b, 1, BF16)
+    assert (g16.float() - torch.nn.functional.gelu(ref)).abs().max().item() <= 1e-2 * scale, "gelu bf16"
+    x0 = torch.randn(M, N, device="cuda")
+    r32 = _run(A, W, b, 2, F32, out=x0.clone())
+    assert (r32 - (x0 + ref)).abs().max().item() <= 3e-5 * scale, "residual f32"
+    nb = _run(A, W, None, 0, F32)
+    assert (nb - (ref - b)).abs().max().item() <= 3e-5 * scale, "no bias"
+    # same answer as the SIMT kernel (the exact-fp32-accumulation reference path)
+    s32 = _run(A, W, b, 0, F32, impl=1)
+    assert (o32 - s32).abs().max().item() <= 3e-5 * scale
+
+
+def test_gemm_tc_full_batch_shape_linearity():
+    """configs[1] size (M = 64 x 1500): property check instead of a dense reference — linearity in A and row independence."""
+    torch.manual_seed(0)
+    M, N, K = 96000, 1280, 1280
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    full = _run(A, W, None, 0, F32)
+    idx = torch.tensor([0, 127, 128, 5000, 77777, 95999], device="cuda")
+    ref = torch.nn.functional.linear(A[idx].float(), W.float())
+    assert (full[idx] - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+    twice = _run((A.float() * 2).bfloat16(), W, None, 0, F32)   # x2 is exact in bf16
+    assert torch.equal(twice, full * 2)
