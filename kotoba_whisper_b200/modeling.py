@@ -179,7 +179,7 @@ class WhisperB200ForConditionalGeneration:
             return sd[name].detach().to(torch.float32)
 
         d = c.d_model
-        zeros = torch.zeros(d, dtype=torch.float32)
+        zeros = torch.zeros(d, dtype=torch.float32, device=next(iter(sd.values())).device)
         enc_layers = (_lib.kw_enc_layer_weights * c.encoder_layers)()
         for l in range(c.encoder_layers):
             p, e = f"model.encoder.layers.{l}.", enc_layers[l]

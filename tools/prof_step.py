@@ -1,0 +1,32 @@
+"""One un-warmed pass of the bench workload (log-mel -> encode -> greedy generate) for ncu launch lists / captures.
+    python tools/prof_step.py [--batch 64] [--max-length 128] [--dtype bf16]"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import KOTOBA, SR, synth_audio  # noqa: E402
+from kotoba_whisper_b200 import WhisperB200Config, WhisperB200ForConditionalGeneration, WhisperFeatureExtractorB200  # noqa: E402
+from kotoba_whisper_b200.random_init import random_state_dict  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=64)
+ap.add_argument("--max-length", type=int, default=128)
+ap.add_argument("--dtype", default="bf16")
+ap.add_argument("--steps", type=int, default=1)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+cfg = WhisperB200Config(**KOTOBA)
+model = WhisperB200ForConditionalGeneration.from_state_dict(
+    random_state_dict(cfg, 0, dev), cfg, dtype=torch.bfloat16 if a.dtype == "bf16" else torch.float32,
+    max_batch=a.batch, device=dev)
+fe = WhisperFeatureExtractorB200(feature_size=128, device=dev)
+audio = torch.from_numpy(synth_audio(a.batch, 1000)).to(dev)
+for _ in range(a.steps):
+    feats = fe.logmel_device(audio)
+    ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=a.max_length)
+torch.cuda.synchronize()
+print("ok", tuple(ids.shape))
