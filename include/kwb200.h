@@ -200,6 +200,10 @@ enum {
 void kw_profile_enable(uint32_t category_mask);
 int kw_profile_read(int32_t category, double* total_ms, int64_t* launches, double* work, int32_t reset);
 
+/* Bring-up hook: shared-memory descriptor parameters (bytes) of the MN-major V operand in the tcgen05 attention kernel
+ * (defaults 16 / 1024 / 2048).  Not part of the stable surface. */
+void kw_debug_attention_desc(int32_t v_lbo_bytes, int32_t v_sbo_bytes, int32_t v_kstep_bytes);
+
 /* 0: auto (tcgen05 where eligible), 1: force SIMT GEMMs, 2: force tcgen05 (error if ineligible). Process-wide. */
 void kw_set_gemm_impl(int32_t impl);
 /* counts kernels launched by this library since the last reset (bench.py's gpu_launches) */

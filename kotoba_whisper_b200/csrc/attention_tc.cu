@@ -1,0 +1,267 @@
+// tcgen05 flash attention for the Whisper encoder (non-causal, no mask, head dim 64, q pre-scaled; the arithmetic of
+// sdpa_attention_forward as called at modeling_whisper.py:342-352), bf16 operands, fp32 softmax / accumulation.
+//
+// CTA = one 128-query tile of one (batch, head); two CTAs are resident per SM (80 KB smem, 256 TMEM columns each) so
+// one CTA's softmax overlaps the other's MMAs.  Per 128-key tile:
+//   warp 4  TMA:  K tile and V tile ([128 keys x 64] bf16, 128 B swizzle) via 3D tensor maps over the strided q/k/v views
+//                 (coordinates = column, time, batch; out-of-range rows are zero-filled)
+//   warp 5  MMA:  S = Q K^T        tcgen05.mma M=128 N=128 K=64 (Q, K both K-major)      -> TMEM columns [0,128)
+//                 O += P V         tcgen05.mma M=128 N=64  K=128 (P K-major from smem, V MN-major) -> TMEM columns [128,192)
+//   warps 0-3     one query row per thread: row max over S (tcgen05.ld), rescale of O in TMEM when the running max moves
+//                 (tcgen05.ld / tcgen05.st), p = exp2(s*log2e - m*log2e), row sum, P -> bf16 into swizzled smem.
+// Finally O / l is written as bf16 with one 128-byte row per thread.
+#include <atomic>
+
+#include "tc_common.cuh"
+
+namespace kw {
+
+extern std::atomic<long long> g_launches;
+
+namespace tc {
+
+constexpr int ABQ = 128, ABK = 128, AHD = 64;
+constexpr int TILE_BYTES = 128 * 64 * 2;           // Q, K, V tiles: 16 KB each
+constexpr int P_BYTES = 2 * TILE_BYTES;            // P: two [128 x 64-key] swizzle atoms
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TMEM_COLS = 256;                 // S: 128 columns, O: 64 columns
+constexpr size_t ATT_SMEM = 1024 + 3 * TILE_BYTES + P_BYTES + 128;
+constexpr uint32_t IDESC_S = make_idesc(128, 128, 0, 0);
+constexpr uint32_t IDESC_PV = make_idesc(128, 64, 0, 1);  // B = V is MN-major (head dim contiguous)
+
+struct AttnParams {
+  bf16* out;
+  long long o_sb, o_st;
+  int Tq, Tk;
+  int v_lbo, v_sbo, v_kstep;  // V (MN-major) descriptor parameters, bytes
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = base + TILE_BYTES, sV = base + 2 * TILE_BYTES, sP = base + 3 * TILE_BYTES;
+  const uint32_t bar0 = sP + P_BYTES;
+  const uint32_t q_full = bar0, k_full = bar0 + 8, k_empty = bar0 + 16, v_full = bar0 + 24, v_empty = bar0 + 32,
+                 s_full = bar0 + 40, p_full = bar0 + 48, o_full = bar0 + 56, tmem_slot = bar0 + 64;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + 3 * TILE_BYTES + P_BYTES + 64);
+  uint8_t* P_gen = gen_base + 3 * TILE_BYTES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ABQ, h = blockIdx.y, b = blockIdx.z;
+  const int n_kt = (p.Tk + ABK - 1) / ABK;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+    mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 128); mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, h * AHD, q0, b);
+      for (int j = 0; j < n_kt; ++j) {
+        if (j > 0) mbar_wait(k_empty, (j - 1) & 1);
+        mbar_expect_tx(k_full, TILE_BYTES);
+        tma_load_3d(sK, &tmK, k_full, h * AHD, j * ABK, b);
+        if (j > 0) mbar_wait(v_empty, (j - 1) & 1);
+        mbar_expect_tx(v_full, TILE_BYTES);
+        tma_load_3d(sV, &tmV, v_full, h * AHD, j * ABK, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_kt; ++j) {
+        // S_j = Q K_j^T.  S is free: softmax j-1 finished reading it before p_full(j-1), which PV_{j-1} waited on.
+        mbar_wait(k_full, j & 1);
+        tc_fence_after();
+        const uint64_t dq = make_desc(sQ), dk = make_desc(sK);
+#pragma unroll
+        for (int k = 0; k < AHD / 16; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+        umma_commit(k_empty);
+        umma_commit(s_full);
+        // O += P_j V_j
+        mbar_wait(p_full, j & 1);
+        mbar_wait(v_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ABK / 16; ++k) {
+          const uint64_t dp = make_desc(sP + (k / 4) * TILE_BYTES) + 2 * (k % 4);
+          const uint64_t dv = make_desc_sw128(sV + k * p.v_kstep, p.v_lbo, p.v_sbo);
+          umma_f16(tO, dp, dv, IDESC_PV, (j | k) != 0);
+        }
+        umma_commit(v_empty);
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue: one query row per thread =====================
+    const int r = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.0f;
+    for (int j = 0; j < n_kt; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kbase = j * ABK;
+      const bool tail = kbase + ABK > p.Tk;
+      float mx = m_run;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + c * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c * 32 + i < p.Tk) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = mx;                       // finite: every tile holds >= 1 valid key
+      const float alpha = ex2((m_run - m_new) * LOG2E);  // 0 on the first tile (m_run = -inf)
+      const float mb = m_new * LOG2E;
+      if (j > 0) {
+        // PV_{j-1} has completed: O may be rescaled and P's smem may be overwritten
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + c * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tO + lane_off + c * 32, v);
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+      }
+      float rs = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + c * 32, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2(fmaf(__uint_as_float(v[i]), LOG2E, -mb));
+          float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), LOG2E, -mb));
+          if (tail) {
+            if (kbase + c * 32 + i >= p.Tk) p0 = 0.0f;
+            if (kbase + c * 32 + i + 1 >= p.Tk) p1 = 0.0f;
+          }
+          rs += p0 + p1;
+          pk[i >> 1] = pack_bf16(p0, p1);
+        }
+        // row r, keys [32c, 32c+32): atom = c / 2, 16-byte chunks (c % 2) * 4 + {0..3}, XOR-swizzled with r % 8
+        uint8_t* prow = P_gen + (c >> 1) * TILE_BYTES + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy P stores -> visible to the UMMA (async proxy)
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(o_full, (n_kt - 1) & 1);
+    tc_fence_after();
+    const int t = q0 + r;
+    const float inv = 1.0f / l_run;
+    bf16* orow = p.out + (size_t)b * p.o_sb + (size_t)t * p.o_st + h * AHD;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_off + c * 32, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (t < p.Tq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c * 32 + i) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+}
+
+static int make_map3(CUtensorMap* map, const void* ptr, int B, int T, int H, long long sb, long long st) {
+  cuuint64_t gdim[3] = {(cuuint64_t)H * AHD, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)st * 2, (cuuint64_t)sb * 2};
+  cuuint32_t box[3] = {(cuuint32_t)AHD, 128, 1};
+  return make_map_bf16(map, ptr, 3, gdim, gstride, box);
+}
+
+static int g_v_lbo = 1024, g_v_sbo = 1024, g_v_kstep = 2048;  // N = 64 is one MN block: only the 8-row K-group stride matters
+
+}  // namespace tc
+
+void attention_tc_debug(int lbo, int sbo, int kstep) {
+  tc::g_v_lbo = lbo;
+  tc::g_v_sbo = sbo;
+  tc::g_v_kstep = kstep;
+}
+
+int attention_tc(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, long long q_sb,
+                 long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st, cudaStream_t st) {
+  using namespace tc;
+  if (B < 1 || H < 1 || Tq < 1 || Tk < 1 || H > 65535 || B > 65535) return KW_ERR_UNSUPPORTED;
+  if ((q_st % 8) || (kv_st % 8) || (q_sb % 8) || (kv_sb % 8) || (o_st % 8) || (o_sb % 8)) return KW_ERR_UNSUPPORTED;
+  if (((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) || ((uintptr_t)out & 15)) return KW_ERR_UNSUPPORTED;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = make_map3(&tmQ, q, B, Tq, H, q_sb, q_st);
+  if (rc) return rc;
+  if ((rc = make_map3(&tmK, k, B, Tk, H, kv_sb, kv_st))) return rc;
+  if ((rc = make_map3(&tmV, v, B, Tk, H, kv_sb, kv_st))) return rc;
+  static bool attr = false;
+  if (!attr) {
+    KW_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
+    attr = true;
+  }
+  AttnParams p;
+  p.out = (bf16*)out; p.o_sb = o_sb; p.o_st = o_st; p.Tq = Tq; p.Tk = Tk;
+  p.v_lbo = g_v_lbo; p.v_sbo = g_v_sbo; p.v_kstep = g_v_kstep;
+  dim3 grid(ceil_div(Tq, ABQ), H, B);
+  attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  KW_LAUNCH_OK();
+  ++g_launches;
+  return KW_OK;
+}
+
+}  // namespace kw

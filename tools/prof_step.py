@@ -25,8 +25,11 @@ model = WhisperB200ForConditionalGeneration.from_state_dict(
     max_batch=a.batch, device=dev)
 fe = WhisperFeatureExtractorB200(feature_size=128, device=dev)
 audio = torch.from_numpy(synth_audio(a.batch, 1000)).to(dev)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()   # ncu --profile-from-start off: skip the random-init kernels
 for _ in range(a.steps):
     feats = fe.logmel_device(audio)
     ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=a.max_length)
 torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", tuple(ids.shape))
