@@ -38,9 +38,9 @@ int attention_simt(const void* q, const void* k, const void* v, void* out, int B
 int attention_tc(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, long long q_sb,
                  long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st, cudaStream_t st);
 void attention_tc_debug(int lbo, int sbo, int kstep);
-int dec_self_attn(const float* qkv, void* kc, void* vc, float* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
+int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
                   cudaStream_t st);
-int dec_cross_attn(const float* q, const void* xkv, float* out, int B, int d, int H, int S, kw_dtype t, cudaStream_t st);
+int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int H, int S, kw_dtype t, cudaStream_t st);
 int sample_launch(const float* logits, const unsigned char* flags, const SampleRules& r, int* tokens, int ld_tokens,
                   int B, int pos, int begin_index, int return_ts, int* finished, cudaStream_t st);
 
@@ -121,7 +121,8 @@ struct kw_model {
   void *bufP = nullptr, *bufQ = nullptr, *a = nullptr, *o = nullptr, *enc_out = nullptr;
   float* x = nullptr;
   // decoder workspaces
-  float *dx = nullptr, *da = nullptr, *dqkv = nullptr, *dq = nullptr, *dattn = nullptr, *dh = nullptr, *logits = nullptr;
+  float *dx = nullptr, *dqkv = nullptr, *dq = nullptr, *logits = nullptr;
+  void *da = nullptr, *dattn = nullptr, *dh = nullptr;  // projection operands: model dtype (bf16 feeds the tcgen05 path)
   void* self_k = nullptr;  // [L][B][H][max_t][64]
   void* self_v = nullptr;
   void* xkv = nullptr;  // [L][B*S][2d]
@@ -232,8 +233,8 @@ int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_ru
   m->a = take(szA); m->o = take(szA); m->enc_out = take(szA);
   m->x = (float*)take(szX);
   m->self_k = take(szSelf); m->self_v = take(szSelf); m->xkv = take(szXkv);
-  m->dx = (float*)take(szDec); m->da = (float*)take(szDec); m->dq = (float*)take(szDec); m->dattn = (float*)take(szDec);
-  m->dqkv = (float*)take(szDqkv); m->dh = (float*)take(szDh); m->logits = (float*)take(szLog);
+  m->dx = (float*)take(szDec); m->da = take(szDec); m->dq = (float*)take(szDec); m->dattn = take(szDec);
+  m->dqkv = (float*)take(szDqkv); m->dh = take(szDh); m->logits = (float*)take(szLog);
   m->flags = (unsigned char*)take(al(V));
   m->finished = (int*)take(al(B * 4));
 
@@ -361,21 +362,21 @@ static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int 
   KW_TRY(embed(tokens, ld_tokens, pos, m->w.tok_embed, m->w.dec_pos, m->dx, B, d, c.vocab_size, t, st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const kw_dec_layer_weights& w = m->dec[l];
-    KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, KW_F32, st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, KW_F32, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
+    KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, t, st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
     KW_TRY(dec_self_attn(m->dqkv, (char*)m->self_k + l * self_stride, (char*)m->self_v + l * self_stride, m->dattn, B, d,
                          H, MT, pos, t, st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, KW_F32, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
-    KW_TRY(layernorm(m->dx, w.lnx_w, w.lnx_b, m->da, B, d, KW_F32, st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, KW_F32, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, t, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+    KW_TRY(layernorm(m->dx, w.lnx_w, w.lnx_b, m->da, B, d, t, st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), st));
     {
       ProfScope ps(KW_PROF_DEC_CROSS, (double)B * S * 2 * d * esize(t), st);  // algorithmic bytes: K and V read once
       KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st));
     }
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, KW_F32, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
-    KW_TRY(layernorm(m->dx, w.ln3_w, w.ln3_b, m->da, B, d, KW_F32, st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, KW_F32, w.w1, t, w.b1, m->dh, F, KW_F32, B, F, d, EPI_GELU), st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dh, F, KW_F32, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, t, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+    KW_TRY(layernorm(m->dx, w.ln3_w, w.ln3_b, m->da, B, d, t, st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.w1, t, w.b1, m->dh, F, t, B, F, d, EPI_GELU), st));
+    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dh, F, t, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), st));
   }
   return KW_OK;
 }
@@ -389,9 +390,9 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
   const kw_config& c = m->cfg;
   KW_TRY(decode_hidden(m, tokens, ld_tokens, B, pos, st));
   if (!sample && !logits_out) return KW_OK;
-  KW_TRY(layernorm(m->dx, m->w.dec_ln_w, m->w.dec_ln_b, m->da, B, c.d_model, KW_F32, st));
+  KW_TRY(layernorm(m->dx, m->w.dec_ln_w, m->w.dec_ln_b, m->da, B, c.d_model, m->t, st));
   float* lg = logits_out ? logits_out : m->logits;
-  KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, c.d_model, KW_F32, m->w.tok_embed, m->t, nullptr, lg, c.vocab_size, KW_F32, B, c.vocab_size,
+  KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, c.d_model, m->t, m->w.tok_embed, m->t, nullptr, lg, c.vocab_size, KW_F32, B, c.vocab_size,
                  c.d_model, EPI_STORE), st));
   if (sample) {
     KW_REQUIRE(finished, "kw_decode_step: sample requires the finished array");

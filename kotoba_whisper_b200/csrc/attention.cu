@@ -183,10 +183,10 @@ int attention_simt(const void* q, const void* k, const void* v, void* out, int B
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Decoder self-attention, one position.  qkv f32 [B, 3d] (q pre-scaled | k | v) from the fused projection;
-// pools kc/vc typed [B, H, max_t, 64].  CTA = (head, batch), 128 threads.
+// pools kc/vc typed [B, H, max_t, 64]; out typed [B, d] (the next projection's operand).  CTA = (head, batch), 128 threads.
 template <typename T>
 __global__ void __launch_bounds__(128)
-dec_self_attn_kernel(const float* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc, float* __restrict__ out,
+dec_self_attn_kernel(const float* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc, T* __restrict__ out,
                      int d, int H, int max_t, int pos) {
   __shared__ float s_q[HD];
   __shared__ float s_p[512];
@@ -237,15 +237,15 @@ dec_self_attn_kernel(const float* __restrict__ qkv, T* __restrict__ kc, T* __res
   for (int j = half; j < n; j += 2) acc = fmaf(s_p[j], ld_f(vp + (size_t)j * HD + e), acc);
   s_o[half][e] = acc;
   __syncthreads();
-  if (tid < HD) out[(size_t)b * d + h * HD + tid] = (s_o[0][tid] + s_o[1][tid]) * inv;
+  if (tid < HD) st_f(out + (size_t)b * d + h * HD + tid, (s_o[0][tid] + s_o[1][tid]) * inv);
 }
 
-int dec_self_attn(const float* qkv, void* kc, void* vc, float* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
+int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
                   cudaStream_t st) {
   KW_REQUIRE(pos >= 0 && pos < max_t && max_t <= 512, "dec_self_attn: pos=%d max_t=%d", pos, max_t);
   dim3 grid(H, B);
-  if (t == KW_BF16) dec_self_attn_kernel<bf16><<<grid, 128, 0, st>>>(qkv, (bf16*)kc, (bf16*)vc, out, d, H, max_t, pos);
-  else dec_self_attn_kernel<float><<<grid, 128, 0, st>>>(qkv, (float*)kc, (float*)vc, out, d, H, max_t, pos);
+  if (t == KW_BF16) dec_self_attn_kernel<bf16><<<grid, 128, 0, st>>>(qkv, (bf16*)kc, (bf16*)vc, (bf16*)out, d, H, max_t, pos);
+  else dec_self_attn_kernel<float><<<grid, 128, 0, st>>>(qkv, (float*)kc, (float*)vc, (float*)out, d, H, max_t, pos);
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;
@@ -272,7 +272,7 @@ __device__ __forceinline__ void load8(const bf16* p, float* f) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, float* __restrict__ out, int d, int S) {
+dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T* __restrict__ out, int d, int S) {
   extern __shared__ float s_p[];  // [S]
   __shared__ float s_red[8];
   __shared__ float s_o[8][HD];
@@ -350,16 +350,16 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, fl
     float acc = 0.0f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) acc += s_o[w][tid];
-    out[(size_t)b * d + h * HD + tid] = acc * inv;
+    st_f(out + (size_t)b * d + h * HD + tid, acc * inv);
   }
 }
 
-int dec_cross_attn(const float* q, const void* xkv, float* out, int B, int d, int H, int S, kw_dtype t,
+int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int H, int S, kw_dtype t,
                    cudaStream_t st) {
   dim3 grid(H, B);
   const size_t smem = sizeof(float) * S;
-  if (t == KW_BF16) dec_cross_attn_kernel<bf16><<<grid, 256, smem, st>>>(q, (const bf16*)xkv, out, d, S);
-  else dec_cross_attn_kernel<float><<<grid, 256, smem, st>>>(q, (const float*)xkv, out, d, S);
+  if (t == KW_BF16) dec_cross_attn_kernel<bf16><<<grid, 256, smem, st>>>(q, (const bf16*)xkv, (bf16*)out, d, S);
+  else dec_cross_attn_kernel<float><<<grid, 256, smem, st>>>(q, (const float*)xkv, (float*)out, d, S);
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

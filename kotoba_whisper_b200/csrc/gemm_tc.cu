@@ -193,6 +193,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode-time ("skinny") variant: M = batch <= 64 rows of activations against a weight matrix that is read exactly once.
+// The product is computed transposed, out^T[N, M] = W[N,K] . A[M,K]^T, so the 128-row MMA dimension streams weight
+// rows and the batch is the N = 64 dimension: 128 x 64 x K tiles, 8-stage ring (128 KB of weights in flight per SM —
+// this kernel is HBM-bound), two 64-column TMEM accumulators.  Epilogue: thread = output feature, lanes = 32 consecutive
+// features, so each per-batch-row store is a coalesced 128 B (fp32) / 64 B (bf16) segment.
+namespace sk {
+constexpr int BM = 128, BN = 64, STAGES = 8;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int TMEM_COLS = 128;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
+constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
+}  // namespace sk
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params p) {
+  constexpr int BM = sk::BM, BN = sk::BN, STAGES = sk::STAGES, A_BYTES = sk::A_BYTES, STAGE_BYTES = sk::STAGE_BYTES;
+  constexpr int TMEM_COLS = sk::TMEM_COLS;
+  constexpr uint32_t IDESC = sk::IDESC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.N + BM - 1) / BM;  // tiles over output features
+  const int k_blocks = p.K / BK;
+
+  if (warp == 4 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), N_EPI_WARPS * 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          const uint32_t sa = base + s * STAGE_BYTES;
+          tma_load_2d(sa, &tmW, full_bar(s), kb * BK, t * BM);
+          tma_load_2d(sa + A_BYTES, &tmA, full_bar(s), kb * BK, 0);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+        const uint32_t as = tcount & 1;
+        mbar_wait(tempty_bar(as), ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar(s), (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint64_t da = make_desc(sa), db = make_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else {
+    uint32_t tcount = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      const uint32_t as = tcount & 1;
+      mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
+      tc_fence_after();
+      const int n = t * BM + warp * 32 + lane;  // output feature owned by this thread
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
+      const float bias = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= p.M) break;  // warp-uniform: no batch rows in this half
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int brow = c * 32 + j;
+            if (brow < p.M) {
+              float v = __uint_as_float(r[j]) + bias;
+              if (p.epi == EPI_GELU) v = gelu_erf(v);
+              const size_t o = (size_t)brow * p.ldo + n;
+              if (p.out_bf16) {
+                reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(v);
+              } else {
+                float* of = reinterpret_cast<float*>(p.out);
+                of[o] = (p.epi == EPI_RESID) ? of[o] + v : v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // 2D bf16 row-major [rows, cols] (ld elements between rows) -> tiles of box_rows x 64 columns
 static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -206,14 +336,11 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
 int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   using namespace tc;
   if (g.a_type != KW_BF16 || g.w_type != KW_BF16) return KW_ERR_UNSUPPORTED;
-  if (g.K % BK != 0 || g.N % 32 != 0 || g.lda % 8 != 0 || g.ldo % 8 != 0 || g.M < 1) return KW_ERR_UNSUPPORTED;
-  if (((uintptr_t)g.A & 15) || ((uintptr_t)g.W & 15) || ((uintptr_t)g.out & 15)) return KW_ERR_UNSUPPORTED;
+  const bool skinny = g.M <= sk::BN && g.epi != EPI_GELU_POS;
+  if (g.K % BK != 0 || g.lda % 8 != 0 || g.M < 1) return KW_ERR_UNSUPPORTED;
+  if (!skinny && (g.N % 32 != 0 || g.ldo % 8 != 0 || ((uintptr_t)g.out & 15))) return KW_ERR_UNSUPPORTED;
+  if (((uintptr_t)g.A & 15) || ((uintptr_t)g.W & 15)) return KW_ERR_UNSUPPORTED;
   if ((g.epi == EPI_RESID || g.epi == EPI_GELU_POS) && g.out_type != KW_F32) return KW_ERR_UNSUPPORTED;
-  CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, g.A, g.M, g.K, g.lda, BM);
-  if (rc) return rc;
-  rc = make_map(&tmB, g.W, g.N, g.K, g.K, BN);
-  if (rc) return rc;
   static int n_sm = 0;
   static bool attr = false;
   if (!attr) {
@@ -221,12 +348,29 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     KW_CUDA_OK(cudaGetDevice(&dev));
     KW_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sk::SMEM_BYTES));
     attr = true;
   }
   Params p;
   p.bias = g.bias; p.out = g.out; p.pos = g.pos;
   p.M = g.M; p.N = g.N; p.K = g.K; p.ldo = g.ldo; p.pos_period = g.pos_period > 0 ? g.pos_period : 1;
   p.epi = g.epi; p.out_bf16 = g.out_type == KW_BF16;
+  CUtensorMap tmA, tmB;
+  if (g.M <= sk::BN && g.epi != EPI_GELU_POS) {  // decode-time shape: weights stream through the 128-row dimension
+    int rc = make_map(&tmB, g.W, g.N, g.K, g.K, sk::BM);
+    if (rc) return rc;
+    if ((rc = make_map(&tmA, g.A, g.M, g.K, g.lda, sk::BN))) return rc;
+    const int tiles = ceil_div(g.N, sk::BM);
+    gemm_tc_skinny_kernel<<<std::min(tiles, n_sm), THREADS, sk::SMEM_BYTES, st>>>(tmB, tmA, p);
+    KW_LAUNCH_OK();
+    ++g_launches;
+    return KW_OK;
+  }
+  int rc = make_map(&tmA, g.A, g.M, g.K, g.lda, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, g.W, g.N, g.K, g.K, BN);
+  if (rc) return rc;
   const int n_tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
   const int grid = std::min(n_tiles, n_sm);
   gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);

@@ -22,7 +22,10 @@ def _run(A, W, bias, epi, out_dtype, out=None, impl=2):
 
 
 SHAPES = [(128, 256, 64), (256, 512, 128), (100, 128, 128), (1500, 1280, 1280), (6000, 3840, 1280), (6000, 1280, 384),
-          (3000, 1280, 3840), (1500, 5120, 1280), (1500, 1280, 5120), (333, 192, 576), (4 * 1500, 2560, 1280)]
+          (3000, 1280, 3840), (1500, 5120, 1280), (1500, 1280, 5120), (333, 192, 576), (4 * 1500, 2560, 1280),
+          # decode-time (skinny, transposed-product kernel): M = batch <= 64, any N
+          (64, 3840, 1280), (64, 1280, 5120), (4, 51866, 1280), (1, 1280, 1280), (33, 5120, 1280), (64, 128, 128),
+          (17, 200, 64)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
