@@ -22,7 +22,8 @@ namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int N_EPI_WARPS = 4, THREADS = 32 * (N_EPI_WARPS + 2);
+constexpr int N_EPI_WARPS = 8, THREADS = 32 * (N_EPI_WARPS + 2);   // wide kernel: 8 epilogue warps + TMA + MMA
+constexpr int SK_EPI_WARPS = 4, SK_THREADS = 32 * (SK_EPI_WARPS + 2);  // skinny kernel
 constexpr int TMEM_COLS = 512;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
 
@@ -34,6 +35,22 @@ struct Params {
 };
 
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
+
+// GELU(erf) for bf16 outputs: erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 rounding) with one
+// MUFU.RCP and one MUFU.EX2 instead of libdevice erff's longer polynomial; the fp32 path keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t acc) { umma_f16(d, a, b, IDESC, acc); }
 
@@ -54,7 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
   const int k_blocks = p.K / BK;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == N_EPI_WARPS && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
@@ -67,7 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) {  // one warp allocates all 512 TMEM columns (two 256-column accumulators)
+  if (warp == N_EPI_WARPS + 1) {  // one warp allocates all 512 TMEM columns (two 256-column accumulators)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -77,7 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 4) {
+  if (warp == N_EPI_WARPS) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
@@ -93,7 +110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == N_EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t it = 0, tcount = 0;
@@ -117,26 +134,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (warps 0-3: TMEM lanes 32*warp .. 32*warp+31) =====================
+    // ===================== epilogue: warp w reads TMEM lanes 32*(w%4).. and columns 128*(w/4) .. +128 =====================
+    const int quarter = warp & 3, half = warp >> 2;
     uint32_t tcount = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
       const uint32_t as = tcount & 1;
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int cbeg = half * (BN / 64);  // 4 chunks of 32 columns per warp
+      float4 xr[8];                       // residual prefetch (EPI_RESID): independent of the MMAs, so issue it early
+      const float* xrow = reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo;
+      auto prefetch_resid = [&](int c) {
+        const int col0 = n0 + c * 32;
+        if (p.epi == EPI_RESID && row_ok && col0 < p.N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xr[j] = *reinterpret_cast<const float4*>(xrow + col0 + 4 * j);
+        }
+      };
+      prefetch_resid(cbeg);
       mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row = m0 + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = cbeg; c < cbeg + BN / 64; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < p.M) {
-          float v[32];
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.epi == EPI_RESID) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] += xr[j].x; v[4 * j + 1] += xr[j].y; v[4 * j + 2] += xr[j].z; v[4 * j + 3] += xr[j].w;
+          }
+          if (c + 1 < cbeg + BN / 64) prefetch_resid(c + 1);  // next chunk's residual in flight during this chunk's stores
+        }
+        if (row_ok) {
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -145,8 +182,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (p.epi == EPI_GELU || p.epi == EPI_GELU_POS) {
+            if (p.out_bf16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+            }
           }
           if (p.epi == EPI_GELU_POS) {
             const float* pr = p.pos + (size_t)(row % p.pos_period) * p.N + col0;
@@ -167,28 +209,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           } else {
             float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-            if (p.epi == EPI_RESID) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 x4 = *reinterpret_cast<const float4*>(o + j);
-                *reinterpret_cast<float4*>(o + j) = make_float4(x4.x + v[j], x4.y + v[j + 1], x4.z + v[j + 2], x4.w + v[j + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(tempty_bar(as));  // 128 arrivals hand the accumulator back to the MMA warp
+      mbar_arrive(tempty_bar(as));  // 256 arrivals hand the accumulator back to the MMA warp
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 5) {
+  if (warp == N_EPI_WARPS + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
@@ -207,7 +241,7 @@ constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
 }  // namespace sk
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params p) {
   constexpr int BM = sk::BM, BN = sk::BN, STAGES = sk::STAGES, A_BYTES = sk::A_BYTES, STAGE_BYTES = sk::STAGE_BYTES;
   constexpr int TMEM_COLS = sk::TMEM_COLS;
@@ -236,7 +270,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), N_EPI_WARPS * 32);
+      mbar_init(tempty_bar(s), SK_EPI_WARPS * 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -297,18 +331,31 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         tmem_ld32(taddr + c * 32, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (n < p.N) {
+          const int nrow = min(32, p.M - c * 32);  // batch rows held in this chunk
+          if (p.out_bf16) {
+            bf16* ob = reinterpret_cast<bf16*>(p.out) + (size_t)(c * 32) * p.ldo + n;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int brow = c * 32 + j;
-            if (brow < p.M) {
-              float v = __uint_as_float(r[j]) + bias;
-              if (p.epi == EPI_GELU) v = gelu_erf(v);
-              const size_t o = (size_t)brow * p.ldo + n;
-              if (p.out_bf16) {
-                reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(v);
-              } else {
-                float* of = reinterpret_cast<float*>(p.out);
-                of[o] = (p.epi == EPI_RESID) ? of[o] + v : v;
+            for (int j = 0; j < 32; ++j) {
+              if (j < nrow) {
+                float v = __uint_as_float(r[j]) + bias;
+                if (p.epi == EPI_GELU) v = gelu_fast(v);
+                ob[(size_t)j * p.ldo] = __float2bfloat16_rn(v);
+              }
+            }
+          } else {
+            float* of = reinterpret_cast<float*>(p.out) + (size_t)(c * 32) * p.ldo + n;
+            float x[32];
+            if (p.epi == EPI_RESID) {  // all residual loads first (independent), then add + store
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = (j < nrow) ? of[(size_t)j * p.ldo] : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nrow) {
+                float v = __uint_as_float(r[j]) + bias;
+                if (p.epi == EPI_GELU) v = gelu_erf(v);
+                if (p.epi == EPI_RESID) v += x[j];
+                of[(size_t)j * p.ldo] = v;
               }
             }
           }
@@ -362,7 +409,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (rc) return rc;
     if ((rc = make_map(&tmA, g.A, g.M, g.K, g.lda, sk::BN))) return rc;
     const int tiles = ceil_div(g.N, sk::BM);
-    gemm_tc_skinny_kernel<<<std::min(tiles, n_sm), THREADS, sk::SMEM_BYTES, st>>>(tmB, tmA, p);
+    gemm_tc_skinny_kernel<<<std::min(tiles, n_sm), SK_THREADS, sk::SMEM_BYTES, st>>>(tmB, tmA, p);
     KW_LAUNCH_OK();
     ++g_launches;
     return KW_OK;
