@@ -96,17 +96,21 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // ===================== MMA issuer =====================
     if (lane == 0) {
       mbar_wait(q_full, 0);
-      for (int j = 0; j < n_kt; ++j) {
-        // S_j = Q K_j^T.  S is free: softmax j-1 finished reading it before p_full(j-1), which PV_{j-1} waited on.
+      const uint64_t dq = make_desc(sQ), dk = make_desc(sK);
+      auto issue_S = [&](int j) {  // S_j = Q K_j^T
         mbar_wait(k_full, j & 1);
         tc_fence_after();
-        const uint64_t dq = make_desc(sQ), dk = make_desc(sK);
 #pragma unroll
         for (int k = 0; k < AHD / 16; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
         umma_commit(k_empty);
         umma_commit(s_full);
-        // O += P_j V_j
+      };
+      issue_S(0);
+      for (int j = 0; j < n_kt; ++j) {
+        // p_full(j): the softmax threads have finished reading S_j and written P_j
         mbar_wait(p_full, j & 1);
+        // S_{j+1} goes first so the next softmax can start while P_j V_j is still running on the tensor pipe
+        if (j + 1 < n_kt) issue_S(j + 1);
         mbar_wait(v_full, j & 1);
         tc_fence_after();
 #pragma unroll

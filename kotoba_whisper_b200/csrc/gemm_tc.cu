@@ -25,7 +25,7 @@ constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTE
 constexpr int N_EPI_WARPS = 8, THREADS = 32 * (N_EPI_WARPS + 2);   // wide kernel: 8 epilogue warps + TMA + MMA
 constexpr int SK_EPI_WARPS = 4, SK_THREADS = 32 * (SK_EPI_WARPS + 2);  // skinny kernel
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 
 struct Params {
   const float* bias;
@@ -40,7 +40,8 @@ constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
 // MUFU.RCP and one MUFU.EX2 instead of libdevice erff's longer polynomial; the fp32 path keeps erff.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));  // 1 MUFU (the IEEE __frcp_rn is ~10 instr)
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -66,6 +67,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 256);  // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
@@ -153,6 +156,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       prefetch_resid(cbeg);
+      {  // this tile's 256 bias values -> smem (one per epilogue thread); reads below are conflict-free broadcasts
+        const int col = n0 + threadIdx.x;
+        s_bias[as * BN + threadIdx.x] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
@@ -174,11 +182,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (c + 1 < cbeg + BN / 64) prefetch_resid(c + 1);  // next chunk's residual in flight during this chunk's stores
         }
         if (row_ok) {
-          if (p.bias) {
+          {
+            const float4* b4p = reinterpret_cast<const float4*>(s_bias + as * BN + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = b4p[j];
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
             }
           }
           if (p.epi == EPI_GELU || p.epi == EPI_GELU_POS) {
