@@ -116,3 +116,23 @@ def test_whisper_oracle_matches_hf_golden_fullsize(golden, name, arch, spec, see
     with torch.no_grad():
         ids = ref.generate(mel, language="ja", task="transcribe", return_timestamps=True, max_length=128)
     assert np.array_equal(ids.numpy(), g[f"{name}_ids_ts1_ml128_ja_transcribe"])
+
+
+def test_chunking_oracle_matches_hf():
+    from transformers.models.whisper.tokenization_whisper import _find_longest_common_sequence
+    from transformers.pipelines.automatic_speech_recognition import chunk_iter
+    from oracle.chunking_ref import chunk_bounds, longest_common_sequence_merge
+
+    class FakeFE:
+        sampling_rate = 16000
+
+        def __call__(self, chunk, **kw):
+            return {"n": len(chunk)}
+
+    for n in (1000, 240000, 400001, 16000 * 100):
+        want = [d["stride"] for d in chunk_iter(np.zeros(n, np.float32), FakeFE(), 240000, 40000, 40000)]
+        assert [s for _, _, s in chunk_bounds(n, 240000, 40000, 40000)] == want
+    rng = np.random.default_rng(4)
+    for _ in range(50):
+        seqs = [rng.integers(0, 12, size=int(rng.integers(3, 30))).tolist() for _ in range(int(rng.integers(1, 5)))]
+        assert longest_common_sequence_merge(seqs) == _find_longest_common_sequence(seqs)
