@@ -192,6 +192,7 @@ dec_self_attn_kernel(const float* __restrict__ qkv, T* __restrict__ kc, T* __res
   __shared__ float s_p[512];
   __shared__ float s_red[4];
   __shared__ float s_o[2][HD];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // lets a PDL-launched projection start its prologue
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const float* row = qkv + (size_t)b * 3 * d;
   T* kp = kc + ((size_t)b * H + h) * max_t * HD;
@@ -253,7 +254,7 @@ int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d,
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Decoder cross-attention, one position.  q f32 [B, d] (pre-scaled); xkv typed [B*S, 2d] = [K | V] rows of the one-shot
-// projection (row stride 2d); out f32 [B, d].  CTA = (head, batch), 256 threads.  8 lanes share one key row with one
+// projection (row stride 2d); out typed [B, d].  CTA = (head, batch), 128 threads.  8 lanes share one key row with one
 // 16 B (bf16) / two 16 B (f32) loads each, so every K/V byte is fetched exactly once with full 32 B sectors.
 __device__ __forceinline__ void load8(const float* p, float* f) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
@@ -270,12 +271,43 @@ __device__ __forceinline__ void load8(const bf16* p, float* f) {
   }
 }
 
+constexpr int XA_THREADS = 128, XA_WARPS = XA_THREADS / 32, XA_UNROLL = 4;
+
+// 8 consecutive elements kept in their storage format until use (4 registers for bf16) so XA_UNROLL rows fit in flight
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float* f) const {
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h2[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void unpack(float* f) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(XA_THREADS, 10)
 dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T* __restrict__ out, int d, int S) {
+  // 128-thread CTAs: all B*H CTAs (1280 at B = 64) are resident at once (<= 16 per SM), so there is no partial second
+  // wave; each warp keeps XA_UNROLL independent 16-byte loads per lane in flight.
   extern __shared__ float s_p[];  // [S]
-  __shared__ float s_red[8];
-  __shared__ float s_o[8][HD];
+  __shared__ float s_red[XA_WARPS];
+  __shared__ float s_o[XA_WARPS][HD];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, sub = lane >> 3, l8 = lane & 7;
   const size_t ld = 2 * (size_t)d;
@@ -283,23 +315,33 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T*
   const T* vbase = kbase + d;
   float qf[8];
   load8(q + (size_t)b * d + h * HD + l8 * 8, qf);
+  constexpr int KEYS_PER_ITER = XA_WARPS * 4 * XA_UNROLL;  // 64 keys per CTA iteration
 
   float lmax = -INFINITY;
-  for (int j0 = warp * 4; j0 < S; j0 += 32) {  // 8 warps x 4 keys per iteration
-    const int j = j0 + sub;
-    float acc = 0.0f;
-    if (j < S) {
-      float kf[8];
-      load8(kbase + (size_t)j * ld, kf);
+  for (int j0 = 0; j0 < S; j0 += KEYS_PER_ITER) {
+    Raw8<T> kr[XA_UNROLL];
+    int jj[XA_UNROLL];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], kf[e], acc);
+    for (int u = 0; u < XA_UNROLL; ++u) {
+      jj[u] = j0 + (u * XA_WARPS + warp) * 4 + sub;
+      if (jj[u] < S) kr[u].load(kbase + (size_t)jj[u] * ld);
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    if (j < S) {
-      if (l8 == 0) s_p[j] = acc;
-      lmax = fmaxf(lmax, acc);
+#pragma unroll
+    for (int u = 0; u < XA_UNROLL; ++u) {
+      float acc = 0.0f;
+      if (jj[u] < S) {
+        float kf[8];
+        kr[u].unpack(kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], kf[e], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (jj[u] < S) {
+        if (l8 == 0) s_p[jj[u]] = acc;
+        lmax = fmaxf(lmax, acc);
+      }
     }
   }
   lmax = warp_max(lmax);
@@ -307,10 +349,10 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T*
   __syncthreads();
   float mx = s_red[0];
 #pragma unroll
-  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
+  for (int i = 1; i < XA_WARPS; ++i) mx = fmaxf(mx, s_red[i]);
   __syncthreads();
   float lsum = 0.0f;
-  for (int j = tid; j < S; j += 256) {
+  for (int j = tid; j < S; j += XA_THREADS) {
     float p = exp_t<T>(s_p[j] - mx);
     s_p[j] = p;
     lsum += p;
@@ -320,20 +362,29 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T*
   __syncthreads();
   float tot = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) tot += s_red[i];
+  for (int i = 0; i < XA_WARPS; ++i) tot += s_red[i];
   const float inv = 1.0f / tot;
 
   float o[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) o[e] = 0.0f;
-  for (int j0 = warp * 4; j0 < S; j0 += 32) {
-    const int j = j0 + sub;
-    if (j < S) {
-      float vf[8];
-      load8(vbase + (size_t)j * ld, vf);
-      const float p = s_p[j];
+  for (int j0 = 0; j0 < S; j0 += KEYS_PER_ITER) {
+    Raw8<T> vr[XA_UNROLL];
+    int jj[XA_UNROLL];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = fmaf(p, vf[e], o[e]);
+    for (int u = 0; u < XA_UNROLL; ++u) {
+      jj[u] = j0 + (u * XA_WARPS + warp) * 4 + sub;
+      if (jj[u] < S) vr[u].load(vbase + (size_t)jj[u] * ld);
+    }
+#pragma unroll
+    for (int u = 0; u < XA_UNROLL; ++u) {
+      if (jj[u] < S) {
+        const float p = s_p[jj[u]];
+        float vf[8];
+        vr[u].unpack(vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(p, vf[e], o[e]);
+      }
     }
   }
 #pragma unroll
@@ -349,7 +400,7 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T*
   if (tid < HD) {
     float acc = 0.0f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) acc += s_o[w][tid];
+    for (int w = 0; w < XA_WARPS; ++w) acc += s_o[w][tid];
     st_f(out + (size_t)b * d + h * HD + tid, acc * inv);
   }
 }
@@ -358,8 +409,8 @@ int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int
                    cudaStream_t st) {
   dim3 grid(H, B);
   const size_t smem = sizeof(float) * S;
-  if (t == KW_BF16) dec_cross_attn_kernel<bf16><<<grid, 256, smem, st>>>(q, (const bf16*)xkv, (bf16*)out, d, S);
-  else dec_cross_attn_kernel<float><<<grid, 256, smem, st>>>(q, (const float*)xkv, (float*)out, d, S);
+  if (t == KW_BF16) dec_cross_attn_kernel<bf16><<<grid, XA_THREADS, smem, st>>>(q, (const bf16*)xkv, (bf16*)out, d, S);
+  else dec_cross_attn_kernel<float><<<grid, XA_THREADS, smem, st>>>(q, (const float*)xkv, (float*)out, d, S);
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

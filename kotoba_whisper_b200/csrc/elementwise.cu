@@ -68,6 +68,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, T* __restrict__ out, int rows,
                                                         int d) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // lets a PDL-launched projection start its prologue
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;

@@ -266,6 +266,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BM - 1) / BM;  // tiles over output features
   const int k_blocks = p.K / BK;
@@ -291,16 +292,26 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 
   if (warp == 4) {
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
-          const uint32_t sa = base + s * STAGE_BYTES;
-          tma_load_2d(sa, &tmW, full_bar(s), kb * BK, t * BM);
-          tma_load_2d(sa + A_BYTES, &tmA, full_bar(s), kb * BK, 0);
-        }
+      const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const uint32_t total = (uint32_t)my_tiles * k_blocks;
+      auto tile_of = [&](uint32_t it) { return (int)blockIdx.x + (int)(it / k_blocks) * (int)gridDim.x; };
+      // Programmatic dependent launch: weights do not depend on the preceding kernel, so the first ring of weight
+      // tiles is requested before griddepcontrol.wait; only the activation tiles wait for the producer grid.
+      const uint32_t pre = total < (uint32_t)STAGES ? total : (uint32_t)STAGES;
+      for (uint32_t it = 0; it < pre; ++it) {
+        mbar_expect_tx(full_bar(it), STAGE_BYTES);
+        tma_load_2d(base + it * STAGE_BYTES, &tmW, full_bar(it), (it % k_blocks) * BK, tile_of(it) * BM);
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      for (uint32_t it = 0; it < pre; ++it)
+        tma_load_2d(base + it * STAGE_BYTES + A_BYTES, &tmA, full_bar(it), (it % k_blocks) * BK, 0);
+      for (uint32_t it = pre; it < total; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const uint32_t sa = base + s * STAGE_BYTES;
+        tma_load_2d(sa, &tmW, full_bar(s), (it % k_blocks) * BK, tile_of(it) * BM);
+        tma_load_2d(sa + A_BYTES, &tmA, full_bar(s), (it % k_blocks) * BK, 0);
       }
     }
   } else if (warp == 5) {
@@ -325,6 +336,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       }
     }
   } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // outputs / residual belong to the preceding kernels
     uint32_t tcount = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const uint32_t as = tcount & 1;
@@ -418,7 +430,18 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (rc) return rc;
     if ((rc = make_map(&tmA, g.A, g.M, g.K, g.lda, sk::BN))) return rc;
     const int tiles = ceil_div(g.N, sk::BM);
-    gemm_tc_skinny_kernel<<<std::min(tiles, n_sm), SK_THREADS, sk::SMEM_BYTES, st>>>(tmB, tmA, p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(std::min(tiles, n_sm));
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = sk::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue + weight prefetch overlap the
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;           // preceding kernel's tail (PDL)
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel, tmB, tmA, p));
     KW_LAUNCH_OK();
     ++g_launches;
     return KW_OK;

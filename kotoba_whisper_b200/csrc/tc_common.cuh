@@ -2,7 +2,10 @@
 #pragma once
 #include <cuda.h>
 
+#include <string.h>
+
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -147,8 +150,42 @@ static EncodeTiledFn get_encode() {
 
 
 // bf16 tensor map, 128 B swizzle, zero OOB fill.  rank 2: [rows, cols]; rank 3: [batch, rows, cols]; strides in elements.
+struct MapKey {
+  const void* ptr;
+  unsigned long long gdim[3], gstride[2];
+  unsigned box[3];
+  int rank;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return h;
+  }
+};
+
+// Encoded tensor maps are cached: workspaces and weights keep their addresses for the life of a model handle, so the
+// ~27 projections of every decode step hit the cache instead of calling into the driver.
 static inline int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* gdim,
                                 const cuuint64_t* gstride_bytes, const cuuint32_t* box) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) { key.gdim[i] = gdim[i]; key.box[i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) key.gstride[i] = gstride_bytes[i];
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *map = it->second;
+      return KW_OK;
+    }
+  }
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("tc: cuTensorMapEncodeTiled not available from the driver");
@@ -162,6 +199,9 @@ static inline int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, con
     set_error("tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return KW_ERR_CUDA;
   }
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *map;
   return KW_OK;
 }
 

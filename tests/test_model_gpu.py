@@ -146,3 +146,30 @@ def test_kotoba_fp32_tokens_bit_identical(golden):
 def test_teacher_fp32_tokens_bit_identical(golden):
     """configs[2] architecture (32 decoder layers) at the CPU-runnable batch the golden was taken on."""
     _check_fullsize(golden, "teacher", TEACHER, "GS", 3000, [(True, 128)], max_batch=2)
+
+
+@pytest.mark.parametrize("arch", [TINY, TINY80])
+def test_bf16_tensor_path_matches_simt_path(arch):
+    """Same bf16 model through the tcgen05 kernels (GEMM, skinny GEMM with PDL, attention) and through the SIMT kernels:
+    encoder output, per-position logits and greedy tokens must agree to bf16-rounding level."""
+    from kotoba_whisper_b200 import _lib
+    lib = _lib.load()
+    model, _ = build_pair(arch, torch.bfloat16, max_batch=4)
+    mel = torch.from_numpy(logmel_batch_f64(clips("UGS", 7), arch["num_mel_bins"])).cuda()
+    toks = torch.tensor([[50258, 50266, 50360, 50365, 11, 12]] * 3, dtype=torch.int32, device="cuda")
+    res = {}
+    for impl in (0, 1):
+        lib.kw_set_gemm_impl(impl)
+        enc = model.encode(mel)
+        model.cross_kv(3)
+        lg = torch.stack([model.step_logits(toks, pos) for pos in range(6)])
+        ids = model.generate(mel, language="ja", task="transcribe", return_timestamps=True, max_length=48)
+        res[impl] = (enc.clone(), lg.clone(), ids.clone())
+    lib.kw_set_gemm_impl(0)
+    enc_t, lg_t, ids_t = res[0]
+    enc_s, lg_s, ids_s = res[1]
+    assert _rel(enc_t, enc_s) <= 3e-2
+    cos = torch.nn.functional.cosine_similarity(enc_t.flatten(1), enc_s.flatten(1), dim=1)
+    assert cos.min() >= 0.9995
+    assert _rel(lg_t, lg_s) <= 3e-2
+    print("bf16 tc vs simt greedy tokens identical:", torch.equal(ids_t, ids_s))
