@@ -1,7 +1,8 @@
 // tcgen05 flash attention for the Whisper encoder (non-causal, no mask, head dim 64, q pre-scaled; the arithmetic of
 // sdpa_attention_forward as called at modeling_whisper.py:342-352), bf16 operands, fp32 softmax / accumulation.
 //
-// CTA = one 128-query tile of one (batch, head), one CTA per SM (448 of the 512 TMEM columns).  The score tile S and
+// CTA = one 128-query tile of one (batch, head) walking 64-key tiles; two CTAs per SM (256 TMEM columns, 48 KB smem each)
+// so that one CTA's MUFU-bound exp phase overlaps the other's TMEM / barrier latency chain.  The score tile S and
 // the probability tile P are both double buffered in TENSOR MEMORY: the tensor pipe computes S(j+1) while the softmax
 // threads work on S(j), and P(j) V(j) takes its A operand straight from TMEM (no shared-memory round trip for P, which
 // would otherwise cost 64 KB of smem traffic per tile on top of the Q/K/V operand reads) while they start on S(j+1).
@@ -26,17 +27,18 @@ extern std::atomic<long long> g_launches;
 
 namespace tc {
 
-constexpr int ABQ = 128, ABK = 128, AHD = 64, KV_STAGES = 2;
-constexpr int TILE_BYTES = 128 * 64 * 2;           // Q, K, V tiles: 16 KB each
-constexpr int ATT_SM_WARPS = 16;                   // softmax warps: 4 threads per query row (32 keys each)
+constexpr int ABQ = 128, ABK = 64, AHD = 64, KV_STAGES = 2;
+constexpr int TILE_BYTES = 128 * 64 * 2;           // Q tile: 16 KB
+constexpr int KV_BYTES = ABK * 64 * 2;             // K, V tiles: 8 KB each
+constexpr int ATT_SM_WARPS = 8;                    // softmax warps: 2 threads per query row (32 keys each)
 constexpr int ATT_SM_THREADS = ATT_SM_WARPS * 32;
 constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 2);
-constexpr int ATT_TMEM_COLS = 512;                 // S0, S1: 128 columns each; O: 64; P0, P1: 64 each (bf16 pairs)
-constexpr int TM_O = 256, TM_P = 320;
-constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = OFF_K + KV_STAGES * TILE_BYTES,
-              OFF_BAR = OFF_V + KV_STAGES * TILE_BYTES, OFF_XCHG = OFF_BAR + 256;
-constexpr size_t ATT_SMEM = 1024 + OFF_XCHG + 2 * 4 * 128 * 4;
-constexpr uint32_t IDESC_S = make_idesc(128, 128, 0, 0);
+constexpr int ATT_TMEM_COLS = 256;                 // S0, S1: 64 columns each; O: 64; P0, P1: 32 each (bf16 pairs)
+constexpr int TM_O = 128, TM_P = 192;
+constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = OFF_K + KV_STAGES * KV_BYTES,
+              OFF_BAR = OFF_V + KV_STAGES * KV_BYTES, OFF_XCHG = OFF_BAR + 256;
+constexpr size_t ATT_SMEM = 1024 + OFF_XCHG + 2 * 2 * 128 * 4;
+constexpr uint32_t IDESC_S = make_idesc(128, ABK, 0, 0);
 constexpr uint32_t IDESC_PV = make_idesc(128, 64, 0, 1);  // B = V is MN-major (head dim contiguous)
 
 struct AttnParams {
@@ -51,9 +53,9 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }  // softmax threads only
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // softmax threads only
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -105,11 +107,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int s = j & 1;
         const uint32_t ph = ((j >> 1) & 1) ^ 1;  // passes immediately the first time round
         mbar_wait(k_empty(s), ph);
-        mbar_expect_tx(k_full(s), TILE_BYTES);
-        tma_load_3d(base + OFF_K + s * TILE_BYTES, &tmK, k_full(s), h * AHD, j * ABK, b);
+        mbar_expect_tx(k_full(s), KV_BYTES);
+        tma_load_3d(base + OFF_K + s * KV_BYTES, &tmK, k_full(s), h * AHD, j * ABK, b);
         mbar_wait(v_empty(s), ph);
-        mbar_expect_tx(v_full(s), TILE_BYTES);
-        tma_load_3d(base + OFF_V + s * TILE_BYTES, &tmV, v_full(s), h * AHD, j * ABK, b);
+        mbar_expect_tx(v_full(s), KV_BYTES);
+        tma_load_3d(base + OFF_V + s * KV_BYTES, &tmV, v_full(s), h * AHD, j * ABK, b);
       }
     }
   } else if (warp == W_MMA) {
@@ -122,9 +124,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(k_full(s), (j >> 1) & 1);
         mbar_wait(s_empty(s), ((j >> 1) & 1) ^ 1);  // softmax has pulled S(j-2) out of this buffer
         tc_fence_after();
-        const uint64_t dk = make_desc(base + OFF_K + s * TILE_BYTES);
+        const uint64_t dk = make_desc(base + OFF_K + s * KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < AHD / 16; ++k) umma_f16(tmem_base + s * 128, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+        for (int k = 0; k < AHD / 16; ++k) umma_f16(tmem_base + s * ABK, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
         umma_commit(s_full(s));
         umma_commit(k_empty(s));
       };
@@ -137,8 +139,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < ABK / 16; ++k) {
-          const uint64_t dv = make_desc_sw128(base + OFF_V + s * TILE_BYTES + k * p.v_kstep, p.v_lbo, p.v_sbo);
-          umma_f16_ts(tO, tmem_base + TM_P + s * 64 + k * 8, dv, IDESC_PV, (j | k) != 0);  // 16 keys = 8 packed columns
+          const uint64_t dv = make_desc_sw128(base + OFF_V + s * KV_BYTES + k * p.v_kstep, p.v_lbo, p.v_sbo);
+          umma_f16_ts(tO, tmem_base + TM_P + s * (ABK / 2) + k * 8, dv, IDESC_PV, (j | k) != 0);  // 16 keys = 8 packed columns
         }
         umma_commit(o_full);
         umma_commit(v_empty(s));
@@ -147,10 +149,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else {
     // ===================== softmax / correction / epilogue: four threads per query row =====================
-    const int quarter = warp & 3, kq = warp >> 2;        // TMEM lane quarter, key quarter (32 keys)
+    const int quarter = warp & 3, kq = warp >> 2;        // TMEM lane quarter, key half (32 keys)
     const int r = quarter * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float* s_xchg = reinterpret_cast<float*>(gen_base + OFF_XCHG);  // [2 (tile parity)][4 (key quarter)][128 rows]
+    float* s_xchg = reinterpret_cast<float*>(gen_base + OFF_XCHG);  // [2 (tile parity)][2 (key half)][128 rows]
     const float LOG2E = 1.4426950408889634f;
     float m_run = -INFINITY, l_run = 0.0f;
     for (int j = 0; j < n_kt; ++j) {
@@ -158,7 +160,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_wait(s_full(s), (j >> 1) & 1);
       tc_fence_after();
       uint32_t v[32];
-      tmem_ld32(tmem_base + s * 128 + lane_off + kq * 32, v);
+      tmem_ld32(tmem_base + s * ABK + lane_off + kq * 32, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
       mbar_arrive(s_empty(s));                            // the scores are in registers: S(j+2) may overwrite the buffer
@@ -176,10 +178,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
       }
-      float* xc = s_xchg + s * 512;
+      float* xc = s_xchg + s * 256;
       xc[kq * 128 + r] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       softmax_bar();
-      const float m_tile = fmaxf(fmaxf(xc[r], xc[128 + r]), fmaxf(xc[256 + r], xc[384 + r]));
+      const float m_tile = fmaxf(xc[r], xc[128 + r]);
       const float m_new = fmaxf(m_run, m_tile);           // finite: every tile holds >= 1 valid key
       const float alpha = ex2((m_run - m_new) * LOG2E);   // 0 on the first tile (m_run = -inf)
       const float mb = m_new * LOG2E;
@@ -197,7 +199,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         pk[(i >> 1) + 1] = pack_bf16(p2, p3);
       }
       // keys [32 kq, 32 kq + 32) of the tile = packed columns [16 kq, 16 kq + 16) of the P buffer, this thread's lane
-      tmem_st16(tmem_base + TM_P + s * 64 + lane_off + kq * 16, pk);
+      tmem_st16(tmem_base + TM_P + s * (ABK / 2) + lane_off + kq * 16, pk);
       l_run = l_run * alpha + ((rs0 + rs1) + (rs2 + rs3));
       m_run = m_new;
       if (j > 0) {
@@ -205,12 +207,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          uint32_t o[16];
-          tmem_ld16(tO + lane_off + kq * 16, o);
+          uint32_t o[32];
+          tmem_ld32(tO + lane_off + kq * 32, o);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st16(tO + lane_off + kq * 16, o);
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tO + lane_off + kq * 32, o);
         }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // P (and the rescaled O) are in TMEM
@@ -221,20 +223,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     // total row sum over the four key quarters (same running max on all of them).  Slot parity n_kt & 1 was last used
     // by tile n_kt - 2, whose readers all passed the tile n_kt - 1 barrier.
-    float* xc = s_xchg + (n_kt & 1) * 512;
+    float* xc = s_xchg + (n_kt & 1) * 256;
     xc[kq * 128 + r] = l_run;
     softmax_bar();
-    const float l_all = (xc[r] + xc[128 + r]) + (xc[256 + r] + xc[384 + r]);
+    const float l_all = xc[r] + xc[128 + r];
     const int t = q0 + r;
     const float inv = 1.0f / l_all;
-    bf16* orow = p.out + (size_t)b * p.o_sb + (size_t)t * p.o_st + h * AHD + kq * 16;
+    bf16* orow = p.out + (size_t)b * p.o_sb + (size_t)t * p.o_st + h * AHD + kq * 32;
     {
-      uint32_t o[16];
-      tmem_ld16(tO + lane_off + kq * 16, o);
+      uint32_t o[32];
+      tmem_ld32(tO + lane_off + kq * 32, o);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (t < p.Tq) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 8) {
+        for (int i = 0; i < 32; i += 8) {
           uint4 w;
           w.x = pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
           w.y = pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
@@ -250,10 +252,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == W_MMA) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
 }
 
-static int make_map3(CUtensorMap* map, const void* ptr, int B, int T, int H, long long sb, long long st) {
+static int make_map3(CUtensorMap* map, const void* ptr, int B, int T, int H, long long sb, long long st, int box_rows) {
   cuuint64_t gdim[3] = {(cuuint64_t)H * AHD, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t gstride[2] = {(cuuint64_t)st * 2, (cuuint64_t)sb * 2};
-  cuuint32_t box[3] = {(cuuint32_t)AHD, 128, 1};
+  cuuint32_t box[3] = {(cuuint32_t)AHD, (cuuint32_t)box_rows, 1};
   return make_map_bf16(map, ptr, 3, gdim, gstride, box);
 }
 
@@ -274,10 +276,10 @@ int attention_tc(const void* q, const void* k, const void* v, void* out, int B, 
   if ((q_st % 8) || (kv_st % 8) || (q_sb % 8) || (kv_sb % 8) || (o_st % 8) || (o_sb % 8)) return KW_ERR_UNSUPPORTED;
   if (((uintptr_t)q & 15) || ((uintptr_t)k & 15) || ((uintptr_t)v & 15) || ((uintptr_t)out & 15)) return KW_ERR_UNSUPPORTED;
   CUtensorMap tmQ, tmK, tmV;
-  int rc = make_map3(&tmQ, q, B, Tq, H, q_sb, q_st);
+  int rc = make_map3(&tmQ, q, B, Tq, H, q_sb, q_st, ABQ);
   if (rc) return rc;
-  if ((rc = make_map3(&tmK, k, B, Tk, H, kv_sb, kv_st))) return rc;
-  if ((rc = make_map3(&tmV, v, B, Tk, H, kv_sb, kv_st))) return rc;
+  if ((rc = make_map3(&tmK, k, B, Tk, H, kv_sb, kv_st, ABK))) return rc;
+  if ((rc = make_map3(&tmV, v, B, Tk, H, kv_sb, kv_st, ABK))) return rc;
   static bool attr = false;
   if (!attr) {
     KW_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
