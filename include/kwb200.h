@@ -204,8 +204,15 @@ int kw_profile_read(int32_t category, double* total_ms, int64_t* launches, doubl
  * (defaults 16 / 1024 / 2048).  Not part of the stable surface. */
 void kw_debug_attention_desc(int32_t v_lbo_bytes, int32_t v_sbo_bytes, int32_t v_kstep_bytes);
 
+/* Bring-up hook: when non-NULL, CTA 0 of the decode-time GEMM writes %globaltimer stamps (ns) of its pipeline phases
+ * into this device buffer of 16 uint64 (0 start, 1 weights requested, 2 dependency wait done, 3 first stage landed,
+ * 4 last MMA committed, 8 accumulator visible to the epilogue, 5 epilogue done, 7 all warps done). */
+void kw_debug_gemm_stamps(uint64_t* dev_buffer_16);
+
 /* 0: auto (tcgen05 where eligible), 1: force SIMT GEMMs, 2: force tcgen05 (error if ineligible). Process-wide. */
 void kw_set_gemm_impl(int32_t impl);
+/* 1: wide GEMMs (M >= 256) use the 2-CTA tcgen05 kernel (cta_group::2, 256 x 256 tiles per CTA pair); 0: 1-CTA kernel. */
+void kw_set_gemm_2cta(int32_t on);
 /* counts kernels launched by this library since the last reset (bench.py's gpu_launches) */
 int64_t kw_launch_count(int32_t reset);
 

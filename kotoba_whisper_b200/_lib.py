@@ -62,7 +62,9 @@ SIGNATURES = {
     "kw_sample": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
     "kw_set_gemm_impl": (None, [i32]),
     "kw_launch_count": (i64, [i32]),
+    "kw_set_gemm_2cta": (None, [i32]),
     "kw_debug_attention_desc": (None, [i32, i32, i32]),
+    "kw_debug_gemm_stamps": (None, [vp]),
     "kw_profile_enable": (None, [C.c_uint32]),
     "kw_profile_read": (i32, [i32, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double), i32]),
 }

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkwb200.so")
 SOURCES = ["api.cu", "logmel.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_tc.cu", "attention.cu", "sampling.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+              "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("KW_NVCC_EXTRA", "").split()
 
 
 def _newer(src: str, dst: str) -> bool:

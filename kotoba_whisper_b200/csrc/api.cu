@@ -38,6 +38,8 @@ int attention_simt(const void* q, const void* k, const void* v, void* out, int B
 int attention_tc(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, long long q_sb,
                  long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st, cudaStream_t st);
 void attention_tc_debug(int lbo, int sbo, int kstep);
+void gemm_tc_set_stamps(unsigned long long* p);
+void gemm_tc_set_2cta(int on);
 int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
                   cudaStream_t st);
 int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int H, int S, kw_dtype t, cudaStream_t st);
@@ -136,10 +138,13 @@ extern "C" {
 const char* kw_last_error(void) { return g_err; }
 const char* kw_version(void) { return "kwb200 0.1 (sm_100a)"; }
 void kw_set_gemm_impl(int32_t impl) { g_gemm_impl.store(impl); }
+void kw_set_gemm_2cta(int32_t on) { gemm_tc_set_2cta(on); }
 
 void kw_debug_attention_desc(int32_t v_lbo_bytes, int32_t v_sbo_bytes, int32_t v_kstep_bytes) {
   attention_tc_debug(v_lbo_bytes, v_sbo_bytes, v_kstep_bytes);
 }
+
+void kw_debug_gemm_stamps(uint64_t* dev_buffer_16) { gemm_tc_set_stamps((unsigned long long*)dev_buffer_16); }
 
 void kw_profile_enable(uint32_t category_mask) { g_prof.mask = category_mask; }
 

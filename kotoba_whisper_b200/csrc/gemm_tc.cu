@@ -22,12 +22,17 @@ namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int N_EPI_WARPS = 8, THREADS = 32 * (N_EPI_WARPS + 2);   // wide kernel: 8 epilogue warps + TMA + MMA
+#ifndef KW_EPI_WARPS
+#define KW_EPI_WARPS 8
+#endif
+constexpr int N_EPI_WARPS = KW_EPI_WARPS, THREADS = 32 * (N_EPI_WARPS + 2);  // wide kernels: 16 epilogue warps + TMA + MMA
+constexpr int EPI_THREADS = N_EPI_WARPS * 32, EPI_COLS = BN / (N_EPI_WARPS / 4);  // 64 columns per epilogue warp
 constexpr int SK_EPI_WARPS = 4, SK_THREADS = 32 * (SK_EPI_WARPS + 2);  // skinny kernel
 constexpr int TMEM_COLS = 512;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
 
 struct Params {
+  unsigned long long* stamps;  // debug timeline (globaltimer ns) written by CTA 0, or nullptr
   const float* bias;
   void* out;
   const float* pos;
@@ -54,6 +59,96 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_t acc) { umma_f16(d, a, b, IDESC, acc); }
+
+// Epilogue of one 128 x 256 accumulator tile for epilogue warp (quarter, cgrp): rows m0 + 32*quarter + lane, columns
+// n0 + 64*cgrp .. +64, in chunks of 16 columns (tcgen05.ld x16) to keep the register footprint of 16 epilogue warps
+// under the 113-register budget of a 576-thread CTA.  Waits for the accumulator (tfull), then TMEM -> registers -> bias /
+// GELU / residual / position add -> 16-byte global stores.  Shared by the 1-CTA and 2-CTA kernels.
+__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc, int m0, int n0, int quarter, int cgrp,
+                                              int lane, float* s_bias_stage, uint32_t tfull_addr, uint32_t tfull_parity) {
+  const int row = m0 + quarter * 32 + lane;
+  const bool row_ok = row < p.M;
+  constexpr int NCH = EPI_COLS / 16;
+  const int cbeg = cgrp * NCH;        // chunk index in units of 16 columns
+  float4 xr[4];                       // residual prefetch (EPI_RESID): independent of the MMAs, so issue it early
+  const float* xrow = reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo;
+  auto prefetch_resid = [&](int c) {
+    const int col0 = n0 + c * 16;
+    if (p.epi == EPI_RESID && row_ok && col0 < p.N) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xr[j] = *reinterpret_cast<const float4*>(xrow + col0 + 4 * j);
+    }
+  };
+  prefetch_resid(cbeg);
+  if (threadIdx.x < BN) {  // this tile's 256 bias values -> smem; reads below are conflict-free broadcasts
+    const int col = n0 + threadIdx.x;
+    s_bias_stage[threadIdx.x] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+  mbar_wait(tfull_addr, tfull_parity);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+  for (int c = cbeg; c < cbeg + NCH; ++c) {
+    const int col0 = n0 + c * 16;
+    if (col0 >= p.N) break;  // warp-uniform
+    uint32_t r[16];
+    tmem_ld16(taddr + c * 16, r);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.epi == EPI_RESID) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[4 * j] += xr[j].x; v[4 * j + 1] += xr[j].y; v[4 * j + 2] += xr[j].z; v[4 * j + 3] += xr[j].w;
+      }
+      if (c + 1 < cbeg + NCH) prefetch_resid(c + 1);  // next chunk's residual in flight during this chunk's stores
+    }
+    if (row_ok) {
+      {
+        const float4* b4p = reinterpret_cast<const float4*>(s_bias_stage + c * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = b4p[j];
+          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+        }
+      }
+      if (p.epi == EPI_GELU || p.epi == EPI_GELU_POS) {
+        if (p.out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+        }
+      }
+      if (p.epi == EPI_GELU_POS) {
+        const float* pr = p.pos + (size_t)(row % p.pos_period) * p.N + col0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 q4 = __ldg(reinterpret_cast<const float4*>(pr + j));
+          v[j] += q4.x; v[j + 1] += q4.y; v[j + 2] += q4.z; v[j + 3] += q4.w;
+        }
+      }
+      if (p.out_bf16) {
+        bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+          uint4 w4;
+          w4.x = pack_bf16(v[j], v[j + 1]); w4.y = pack_bf16(v[j + 2], v[j + 3]);
+          w4.z = pack_bf16(v[j + 4], v[j + 5]); w4.w = pack_bf16(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(o + j) = w4;
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
@@ -137,95 +232,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue: warp w reads TMEM lanes 32*(w%4).. and columns 128*(w/4) .. +128 =====================
-    const int quarter = warp & 3, half = warp >> 2;
+    // ===================== epilogue: warp w reads TMEM lanes 32*(w%4).. and columns 64*(w/4) .. +64 =====================
+    const int quarter = warp & 3, cgrp = warp >> 2;
     uint32_t tcount = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
       const uint32_t as = tcount & 1;
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const int cbeg = half * (BN / 64);  // 4 chunks of 32 columns per warp
-      float4 xr[8];                       // residual prefetch (EPI_RESID): independent of the MMAs, so issue it early
-      const float* xrow = reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo;
-      auto prefetch_resid = [&](int c) {
-        const int col0 = n0 + c * 32;
-        if (p.epi == EPI_RESID && row_ok && col0 < p.N) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) xr[j] = *reinterpret_cast<const float4*>(xrow + col0 + 4 * j);
-        }
-      };
-      prefetch_resid(cbeg);
-      {  // this tile's 256 bias values -> smem (one per epilogue thread); reads below are conflict-free broadcasts
-        const int col = n0 + threadIdx.x;
-        s_bias[as * BN + threadIdx.x] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-      mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = cbeg; c < cbeg + BN / 64; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.epi == EPI_RESID) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[4 * j] += xr[j].x; v[4 * j + 1] += xr[j].y; v[4 * j + 2] += xr[j].z; v[4 * j + 3] += xr[j].w;
-          }
-          if (c + 1 < cbeg + BN / 64) prefetch_resid(c + 1);  // next chunk's residual in flight during this chunk's stores
-        }
-        if (row_ok) {
-          {
-            const float4* b4p = reinterpret_cast<const float4*>(s_bias + as * BN + c * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = b4p[j];
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-            }
-          }
-          if (p.epi == EPI_GELU || p.epi == EPI_GELU_POS) {
-            if (p.out_bf16) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-            }
-          }
-          if (p.epi == EPI_GELU_POS) {
-            const float* pr = p.pos + (size_t)(row % p.pos_period) * p.N + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 q4 = __ldg(reinterpret_cast<const float4*>(pr + j));
-              v[j] += q4.x; v[j + 1] += q4.y; v[j + 2] += q4.z; v[j + 3] += q4.w;
-            }
-          }
-          if (p.out_bf16) {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 w4;
-              w4.x = pack_bf16(v[j], v[j + 1]); w4.y = pack_bf16(v[j + 2], v[j + 3]);
-              w4.z = pack_bf16(v[j + 4], v[j + 5]); w4.w = pack_bf16(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = w4;
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-        }
-      }
+      epilogue_tile(p, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN, tfull_bar(as),
+                    (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(tempty_bar(as));  // 256 arrivals hand the accumulator back to the MMA warp
+      mbar_arrive(tempty_bar(as));  // one arrival per epilogue thread hands the accumulator back to the MMA warp
     }
   }
 
@@ -237,24 +253,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Decode-time ("skinny") variant: M = batch <= 64 rows of activations against a weight matrix that is read exactly once.
-// The product is computed transposed, out^T[N, M] = W[N,K] . A[M,K]^T, so the 128-row MMA dimension streams weight
-// rows and the batch is the N = 64 dimension: 128 x 64 x K tiles, 8-stage ring (128 KB of weights in flight per SM —
-// this kernel is HBM-bound), two 64-column TMEM accumulators.  Epilogue: thread = output feature, lanes = 32 consecutive
-// features, so each per-batch-row store is a coalesced 128 B (fp32) / 64 B (bf16) segment.
-namespace sk {
-constexpr int BM = 128, BN = 64, STAGES = 8;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int TMEM_COLS = 128;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256;
-constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
-}  // namespace sk
+// 2-CTA variant (cta_group::2): a pair of CTAs on one TPC computes a 256 x 256 tile with tcgen05.mma M = 256.  Each CTA
+// stages its own 128 rows of A and only HALF of the W tile (128 of the 256 weight rows), so the shared-memory fill and
+// the L2 -> SM traffic per MMA drop by a third (32 KB instead of 48 KB per CTA per k-block), which is what limits the
+// single-CTA kernel.  The leader CTA (cluster rank 0) issues every MMA; both CTAs run a TMA producer that credits the
+// LEADER's full barrier; tcgen05.commit multicasts the "stage free" and "accumulator ready" arrivals to both CTAs; the
+// non-leader's epilogue threads release the accumulator on the leader's barrier through a shared::cluster arrive.
+namespace c2 {
+constexpr int STAGES = 6;
+constexpr int A_BYTES = 128 * BK * 2, B_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA: 32 KB
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + 2 * BN * 4;
+constexpr uint32_t IDESC = make_idesc(256, BN, 0, 0);
+}  // namespace c2
 
-__global__ void __launch_bounds__(SK_THREADS, 1)
-gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params p) {
-  constexpr int BM = sk::BM, BN = sk::BN, STAGES = sk::STAGES, A_BYTES = sk::A_BYTES, STAGE_BYTES = sk::STAGE_BYTES;
-  constexpr int TMEM_COLS = sk::TMEM_COLS;
-  constexpr uint32_t IDESC = sk::IDESC;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  constexpr int STAGES = c2::STAGES, A_BYTES = c2::A_BYTES, STAGE_BYTES = c2::STAGE_BYTES;
+  constexpr uint32_t IDESC = c2::IDESC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = base + STAGES * STAGE_BYTES;
@@ -263,10 +278,142 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+  float* s_bias = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES + 256);  // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles_m = (p.M + 255) / 256, tiles_n = (p.N + BN - 1) / BN, n_tiles = tiles_m * tiles_n;
+  const int k_blocks = p.K / BK;
+
+  if (warp == N_EPI_WARPS && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);    // used in the leader only: one arrive.expect_tx for the pair's 64 KB
+      mbar_init(empty_bar(s), 1);   // one multicast commit per use, in each CTA
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);                       // multicast commit, in each CTA
+      mbar_init(tempty_bar(s), 2 * N_EPI_WARPS * 32);   // leader only: both CTAs' epilogue threads
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == N_EPI_WARPS + 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == N_EPI_WARPS) {
+    // ===================== TMA producer (both CTAs): own 128 rows of A, own half of the W tile =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = pair; t < n_tiles; t += n_pairs) {
+        const int m0 = (t / tiles_n) * 256 + (int)rank * 128, n0 = (t % tiles_n) * BN + (int)rank * 128;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);  // bytes of both CTAs land on this barrier
+          const uint32_t lead_full = mapa_u32(full_bar(s), 0);
+          const uint32_t sa = base + s * STAGE_BYTES;
+          tma_load_2d_2sm(sa, &tmA, lead_full, kb * BK, m0);
+          tma_load_2d_2sm(sa + A_BYTES, &tmB, lead_full, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == N_EPI_WARPS + 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int t = pair; t < n_tiles; t += n_pairs, ++tcount) {
+        const uint32_t as = tcount & 1;
+        mbar_wait(tempty_bar(as), ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full_bar(s), (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t sa = base + s * STAGE_BYTES;
+          const uint64_t da = make_desc(sa), db = make_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
+          umma_commit_2sm(empty_bar(s), 3);  // both CTAs' stage s is reusable once these MMAs have read it
+        }
+        umma_commit_2sm(tfull_bar(as), 3);   // accumulator complete in both CTAs
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int quarter = warp & 3, cgrp = warp >> 2;
+    uint32_t tcount = 0;
+    for (int t = pair; t < n_tiles; t += n_pairs, ++tcount) {
+      const int m0 = (t / tiles_n) * 256 + (int)rank * 128, n0 = (t % tiles_n) * BN;
+      const uint32_t as = tcount & 1;
+      epilogue_tile(p, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN, tfull_bar(as),
+                    (tcount >> 1) & 1);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0));  // both CTAs' epilogue threads hand the accumulator back
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody frees TMEM or exits while the peer may still signal / read
+  if (warp == N_EPI_WARPS + 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode-time ("skinny") variant: M = batch <= 64 rows of activations against a weight matrix that is read exactly once.
+// The product is computed transposed, out^T[N, M] = W[N,K] . A[M,K]^T, so the 128-row MMA dimension streams weight
+// rows and the batch is the N = 64 dimension: 128 x 64 x K tiles, 8-stage ring (128 KB of weights in flight per SM —
+// this kernel is HBM-bound), two 64-column TMEM accumulators.  Epilogue: thread = output feature, lanes = 32 consecutive
+// features, so each per-batch-row store is a coalesced 128 B (fp32) / 64 B (bf16) segment.
+namespace sk {
+constexpr int BM = 128, BN = 64;  // MMA shape: 128 weight rows x 64 batch columns
+// R = weight rows actually loaded (and produced) per tile.  R = 32 quarters the bytes per stage, so small-N projections
+// spread over 4x more CTAs and a 16-stage ring holds a whole K = 1280 slice in ~one round trip; the MMA still runs at
+// M = 128 and simply reads stale shared memory for rows R..127, whose accumulator rows are never read back.
+template <int R> struct Cfg {
+  static constexpr int A_BYTES = R * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = R == 32 ? 16 : 8;
+  static constexpr int RING = STAGES * STAGE_BYTES + (BM - R) * BK * 2;  // + tail the M = 128 read of the last stage may touch
+  static constexpr size_t SMEM_BYTES = 1024 + (size_t)RING + 512;
+};
+constexpr int TMEM_COLS = 128;
+constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
+}  // namespace sk
+
+template <int R>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params p) {
+  using C = sk::Cfg<R>;
+  constexpr int BM = R, BN = sk::BN, STAGES = C::STAGES, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int TMEM_COLS = sk::TMEM_COLS;
+  constexpr uint32_t IDESC = sk::IDESC;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = base + C::RING;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
   uint32_t* tmem_slot_ptr =
-      reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 4));
+      reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + C::RING + 8 * (2 * STAGES + 4));
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  auto stamp = [&](int i) {
+    if (p.stamps && blockIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.stamps[i] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BM - 1) / BM;  // tiles over output features
   const int k_blocks = p.K / BK;
@@ -302,7 +449,9 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         mbar_expect_tx(full_bar(it), STAGE_BYTES);
         tma_load_2d(base + it * STAGE_BYTES, &tmW, full_bar(it), (it % k_blocks) * BK, tile_of(it) * BM);
       }
+      stamp(1);
       asm volatile("griddepcontrol.wait;" ::: "memory");
+      stamp(2);
       for (uint32_t it = 0; it < pre; ++it)
         tma_load_2d(base + it * STAGE_BYTES + A_BYTES, &tmA, full_bar(it), (it % k_blocks) * BK, 0);
       for (uint32_t it = pre; it < total; ++it) {
@@ -325,6 +474,8 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(full_bar(s), (it / STAGES) & 1);
+          if (it == 0) stamp(3);
+          if (it < 40) stamp(16 + it);
           tc_fence_after();
           const uint32_t sa = base + s * STAGE_BYTES;
           const uint64_t da = make_desc(sa), db = make_desc(sa + A_BYTES);
@@ -333,6 +484,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           umma_commit(empty_bar(s));
         }
         umma_commit(tfull_bar(as));
+        stamp(4);
       }
     }
   } else {
@@ -340,18 +492,21 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     uint32_t tcount = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const uint32_t as = tcount & 1;
+      const bool row_warp = warp * 32 < R;        // TMEM lanes R..127 hold garbage rows
+      const int n = t * BM + warp * 32 + lane;    // output feature owned by this thread
+      const bool n_ok = row_warp && n < p.N;
+      const float bias = (p.bias && n_ok) ? __ldg(p.bias + n) : 0.0f;  // in flight while the MMAs finish
       mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
+      if (threadIdx.x == 0 && tcount == 0) stamp(8);
       tc_fence_after();
-      const int n = t * BM + warp * 32 + lane;  // output feature owned by this thread
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
-      const float bias = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.0f;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        if (c * 32 >= p.M) break;  // warp-uniform: no batch rows in this half
+        if (c * 32 >= p.M || !row_warp) break;  // warp-uniform: no batch rows in this half / no valid weight rows
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (n < p.N) {
+        if (n_ok) {
           const int nrow = min(32, p.M - c * 32);  // batch rows held in this chunk
           if (p.out_bf16) {
             bf16* ob = reinterpret_cast<bf16*>(p.out) + (size_t)(c * 32) * p.ldo + n;
@@ -384,12 +539,17 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
+      if (threadIdx.x == 0) { stamp(5 + (tcount == 0 ? 0 : 1)); }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(7);
   if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
 }
+
+static unsigned long long* g_stamps = nullptr;
+static int g_use_2cta = 1;
 
 // 2D bf16 row-major [rows, cols] (ld elements between rows) -> tiles of box_rows x 64 columns
 static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int ld, int box_rows) {
@@ -400,6 +560,9 @@ static int make_map(CUtensorMap* map, const void* ptr, int rows, int cols, int l
 }
 
 }  // namespace tc
+
+void gemm_tc_set_stamps(unsigned long long* p) { tc::g_stamps = p; }
+void gemm_tc_set_2cta(int on) { tc::g_use_2cta = on; }
 
 int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   using namespace tc;
@@ -416,32 +579,53 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     KW_CUDA_OK(cudaGetDevice(&dev));
     KW_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sk::SMEM_BYTES));
+    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sk::Cfg<32>::SMEM_BYTES));
+    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sk::Cfg<128>::SMEM_BYTES));
     attr = true;
   }
   Params p;
+  p.stamps = g_stamps;
   p.bias = g.bias; p.out = g.out; p.pos = g.pos;
   p.M = g.M; p.N = g.N; p.K = g.K; p.ldo = g.ldo; p.pos_period = g.pos_period > 0 ? g.pos_period : 1;
   p.epi = g.epi; p.out_bf16 = g.out_type == KW_BF16;
   CUtensorMap tmA, tmB;
   if (g.M <= sk::BN && g.epi != EPI_GELU_POS) {  // decode-time shape: weights stream through the 128-row dimension
-    int rc = make_map(&tmB, g.W, g.N, g.K, g.K, sk::BM);
+    const int R = g.N <= 8192 ? 32 : 128;  // small projections: 32 weight rows per CTA tile -> 4x the CTAs in flight
+    int rc = make_map(&tmB, g.W, g.N, g.K, g.K, R);
     if (rc) return rc;
     if ((rc = make_map(&tmA, g.A, g.M, g.K, g.lda, sk::BN))) return rc;
-    const int tiles = ceil_div(g.N, sk::BM);
+    const int tiles = ceil_div(g.N, R);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(std::min(tiles, n_sm));
     cfg.blockDim = dim3(SK_THREADS);
-    cfg.dynamicSmemBytes = sk::SMEM_BYTES;
+    cfg.dynamicSmemBytes = R == 32 ? sk::Cfg<32>::SMEM_BYTES : sk::Cfg<128>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue + weight prefetch overlap the
     attrs[0].val.programmaticStreamSerializationAllowed = 1;           // preceding kernel's tail (PDL)
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel, tmB, tmA, p));
+    if (R == 32) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<32>, tmB, tmA, p));
+    else KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<128>, tmB, tmA, p));
+    KW_LAUNCH_OK();
+    ++g_launches;
+    return KW_OK;
+  }
+  if (g_use_2cta && g.M >= 256 && g.K >= 1024) {  // short-K tiles are epilogue-bound: 1-CTA kernel
+    int rc = make_map(&tmA, g.A, g.M, g.K, g.lda, 128);
+    if (rc) return rc;
+    if ((rc = make_map(&tmB, g.W, g.N, g.K, g.K, 128))) return rc;
+    static bool attr2 = false;
+    if (!attr2) {
+      KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c2::SMEM_BYTES));
+      attr2 = true;
+    }
+    const int tiles = ceil_div(g.M, 256) * ceil_div(g.N, BN);
+    const int pairs = std::min(tiles, n_sm / 2);
+    gemm_tc2_kernel<<<2 * pairs, THREADS, c2::SMEM_BYTES, st>>>(tmA, tmB, p);
     KW_LAUNCH_OK();
     ++g_launches;
     return KW_OK;

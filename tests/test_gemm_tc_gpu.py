@@ -64,3 +64,27 @@ def test_gemm_tc_full_batch_shape_linearity():
     assert (full[idx] - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
     twice = _run((A.float() * 2).bfloat16(), W, None, 0, F32)   # x2 is exact in bf16
     assert torch.equal(twice, full * 2)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 256), (1500, 1280, 1280), (6000, 3840, 1280), (6000, 1280, 384),
+                                   (3000, 1280, 3840), (1500, 5120, 1280), (333, 192, 576), (4 * 1500, 2560, 1280)])
+def test_gemm_tc_2cta_matches_torch(M, N, K):
+    """cta_group::2 kernel (CTA pairs, 256 x 256 tiles, M = 256 MMAs): same checks as the 1-CTA kernel."""
+    lib = _lib.load()
+    lib.kw_set_gemm_2cta(1)
+    try:
+        torch.manual_seed(M + N + K)
+        A = torch.randn(M, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda")
+        ref = torch.nn.functional.linear(A.float(), W.float(), b)
+        scale = max(1.0, ref.abs().max().item())
+        o32 = _run(A, W, b, 0, F32)
+        assert (o32 - ref).abs().max().item() <= 3e-5 * scale, "store f32"
+        g16 = _run(A, W, b, 1, BF16)
+        assert (g16.float() - torch.nn.functional.gelu(ref)).abs().max().item() <= 1e-2 * scale, "gelu bf16"
+        x0 = torch.randn(M, N, device="cuda")
+        r32 = _run(A, W, b, 2, F32, out=x0.clone())
+        assert (r32 - (x0 + ref)).abs().max().item() <= 3e-5 * scale, "residual f32"
+    finally:
+        lib.kw_set_gemm_2cta(0)

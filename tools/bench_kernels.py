@@ -41,6 +41,9 @@ def linear(M, N, K, epi, out_dtype, tag):
     print(f"{tag:28s} M={M:6d} N={N:6d} K={K:5d}  {ms*1e3:9.1f} us  {tf:8.1f} TFLOP/s  weights+act {gb:8.1f} GB/s", flush=True)
 
 
+if "2cta" in what:
+    lib.kw_set_gemm_2cta(1)
+    what.append("gemm")
 if "gemm" in what:
     M = 96000
     linear(M, 3840, 1280, 0, BF16, "qkv (store bf16)")
