@@ -181,81 +181,6 @@ int attention_simt(const void* q, const void* k, const void* v, void* out, int B
   return KW_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Decoder self-attention, one position.  qkv f32 [B, 3d] (q pre-scaled | k | v) from the fused projection;
-// pools kc/vc typed [B, H, max_t, 64]; out typed [B, d] (the next projection's operand).  CTA = (head, batch), 128 threads.
-template <typename T>
-__global__ void __launch_bounds__(128)
-dec_self_attn_kernel(const float* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc, T* __restrict__ out,
-                     int d, int H, int max_t, int pos) {
-  __shared__ float s_q[HD];
-  __shared__ float s_p[512];
-  __shared__ float s_red[4];
-  __shared__ float s_o[2][HD];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // lets a PDL-launched projection start its prologue
-  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const float* row = qkv + (size_t)b * 3 * d;
-  T* kp = kc + ((size_t)b * H + h) * max_t * HD;
-  T* vp = vc + ((size_t)b * H + h) * max_t * HD;
-  if (tid < HD) {
-    s_q[tid] = row[h * HD + tid];
-    st_f(kp + (size_t)pos * HD + tid, row[d + h * HD + tid]);
-  } else {
-    st_f(vp + (size_t)pos * HD + (tid - HD), row[2 * d + h * HD + (tid - HD)]);
-  }
-  __syncthreads();  // the new k/v row is visible to the whole CTA (global writes by this CTA, read below by this CTA)
-  const int n = pos + 1;
-  float lmax = -INFINITY;
-  for (int j = tid; j < n; j += 128) {
-    const T* kr = kp + (size_t)j * HD;
-    float acc = 0.0f;
-#pragma unroll
-    for (int e = 0; e < HD; e += 4) {
-      float4 kk = ld4(kr + e);
-      acc = fmaf(s_q[e], kk.x, acc); acc = fmaf(s_q[e + 1], kk.y, acc);
-      acc = fmaf(s_q[e + 2], kk.z, acc); acc = fmaf(s_q[e + 3], kk.w, acc);
-    }
-    s_p[j] = acc;
-    lmax = fmaxf(lmax, acc);
-  }
-  lmax = warp_max(lmax);
-  if ((tid & 31) == 0) s_red[tid >> 5] = lmax;
-  __syncthreads();
-  const float mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-  __syncthreads();
-  float lsum = 0.0f;
-  for (int j = tid; j < n; j += 128) {
-    float p = exp_t<T>(s_p[j] - mx);
-    s_p[j] = p;
-    lsum += p;
-  }
-  lsum = warp_sum(lsum);
-  if ((tid & 31) == 0) s_red[tid >> 5] = lsum;
-  __syncthreads();
-  const float inv = 1.0f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
-  const int e = tid & 63, half = tid >> 6;
-  float acc = 0.0f;
-  for (int j = half; j < n; j += 2) acc = fmaf(s_p[j], ld_f(vp + (size_t)j * HD + e), acc);
-  s_o[half][e] = acc;
-  __syncthreads();
-  if (tid < HD) st_f(out + (size_t)b * d + h * HD + tid, (s_o[0][tid] + s_o[1][tid]) * inv);
-}
-
-int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
-                  cudaStream_t st) {
-  KW_REQUIRE(pos >= 0 && pos < max_t && max_t <= 512, "dec_self_attn: pos=%d max_t=%d", pos, max_t);
-  dim3 grid(H, B);
-  if (t == KW_BF16) dec_self_attn_kernel<bf16><<<grid, 128, 0, st>>>(qkv, (bf16*)kc, (bf16*)vc, (bf16*)out, d, H, max_t, pos);
-  else dec_self_attn_kernel<float><<<grid, 128, 0, st>>>(qkv, (float*)kc, (float*)vc, (float*)out, d, H, max_t, pos);
-  KW_LAUNCH_OK();
-  ++g_launches;
-  return KW_OK;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Decoder cross-attention, one position.  q f32 [B, d] (pre-scaled); xkv typed [B*S, 2d] = [K | V] rows of the one-shot
-// projection (row stride 2d); out typed [B, d].  CTA = (head, batch), 128 threads.  8 lanes share one key row with one
-// 16 B (bf16) / two 16 B (f32) loads each, so every K/V byte is fetched exactly once with full 32 B sectors.
 __device__ __forceinline__ void load8(const float* p, float* f) {
   float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -270,8 +195,6 @@ __device__ __forceinline__ void load8(const bf16* p, float* f) {
     f[2 * i + 1] = t.y;
   }
 }
-
-constexpr int XA_THREADS = 128, XA_WARPS = XA_THREADS / 32, XA_UNROLL = 4;
 
 // 8 consecutive elements kept in their storage format until use (4 registers for bf16) so XA_UNROLL rows fit in flight
 template <typename T> struct Raw8;
@@ -298,6 +221,125 @@ template <> struct Raw8<float> {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
   }
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decoder self-attention, one position.  qkv f32 [B, 3d] (q pre-scaled | k | v) from the fused projection;
+// pools kc/vc typed [B, H, max_t, 64]; out typed [B, d] (the next projection's operand).  CTA = (head, batch), 128 threads.
+template <typename T>
+__global__ void __launch_bounds__(128)
+dec_self_attn_kernel(const float* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc, T* __restrict__ out,
+                     int d, int H, int max_t, int pos) {
+  // 8 lanes share one cached key / value row (16-byte loads, coalesced 128 B per row), 4 rows per warp per load,
+  // 2 loads in flight per lane: the whole <= 448-row history is ~14 dependent-free iterations instead of a per-thread
+  // walk over 64-element rows.
+  __shared__ float s_p[512];
+  __shared__ float s_red[4];
+  __shared__ float s_o[4][HD];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // lets a PDL-launched projection start its prologue
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31, sub = lane >> 3, l8 = lane & 7;
+  const float* row = qkv + (size_t)b * 3 * d;
+  T* kp = kc + ((size_t)b * H + h) * max_t * HD;
+  T* vp = vc + ((size_t)b * H + h) * max_t * HD;
+  if (tid < HD) st_f(kp + (size_t)pos * HD + tid, row[d + h * HD + tid]);
+  else st_f(vp + (size_t)pos * HD + (tid - HD), row[2 * d + h * HD + (tid - HD)]);
+  float qf[8];
+  load8(row + h * HD + l8 * 8, qf);
+  __syncthreads();  // the new k/v row (written by this CTA) is visible to the whole CTA
+  const int n = pos + 1;
+  float lmax = -INFINITY;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    Raw8<T> kr[2];
+    int jj[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      jj[u] = j0 + (u * 4 + warp) * 4 + sub;
+      if (jj[u] < n) kr[u].load(kp + (size_t)jj[u] * HD + l8 * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float acc = 0.0f;
+      if (jj[u] < n) {
+        float kf[8];
+        kr[u].unpack(kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], kf[e], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (jj[u] < n) {
+        if (l8 == 0) s_p[jj[u]] = acc;
+        lmax = fmaxf(lmax, acc);
+      }
+    }
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) s_red[warp] = lmax;
+  __syncthreads();
+  const float mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  float lsum = 0.0f;
+  for (int j = tid; j < n; j += 128) {
+    float p = exp_t<T>(s_p[j] - mx);
+    s_p[j] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) s_red[warp] = lsum;
+  __syncthreads();
+  const float inv = 1.0f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    Raw8<T> vr[2];
+    int jj[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      jj[u] = j0 + (u * 4 + warp) * 4 + sub;
+      if (jj[u] < n) vr[u].load(vp + (size_t)jj[u] * HD + l8 * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (jj[u] < n) {
+        const float p = s_p[jj[u]];
+        float vf[8];
+        vr[u].unpack(vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(p, vf[e], o[e]);
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
+    o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_o[warp][l8 * 8 + e] = o[e];
+  }
+  __syncthreads();
+  if (tid < HD) st_f(out + (size_t)b * d + h * HD + tid, (s_o[0][tid] + s_o[1][tid] + s_o[2][tid] + s_o[3][tid]) * inv);
+}
+
+int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
+                  cudaStream_t st) {
+  KW_REQUIRE(pos >= 0 && pos < max_t && max_t <= 512, "dec_self_attn: pos=%d max_t=%d", pos, max_t);
+  dim3 grid(H, B);
+  if (t == KW_BF16) dec_self_attn_kernel<bf16><<<grid, 128, 0, st>>>(qkv, (bf16*)kc, (bf16*)vc, (bf16*)out, d, H, max_t, pos);
+  else dec_self_attn_kernel<float><<<grid, 128, 0, st>>>(qkv, (float*)kc, (float*)vc, (float*)out, d, H, max_t, pos);
+  KW_LAUNCH_OK();
+  ++g_launches;
+  return KW_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decoder cross-attention, one position.  q f32 [B, d] (pre-scaled); xkv typed [B*S, 2d] = [K | V] rows of the one-shot
+// projection (row stride 2d); out typed [B, d].  CTA = (head, batch), 128 threads.  8 lanes share one key row with one
+// 16 B (bf16) / two 16 B (f32) loads each, so every K/V byte is fetched exactly once with full 32 B sectors.
+constexpr int XA_THREADS = 128, XA_WARPS = XA_THREADS / 32, XA_UNROLL = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(XA_THREADS, 10)

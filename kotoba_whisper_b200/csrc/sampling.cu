@@ -70,8 +70,7 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
   const bool at_begin = s_state[0], last_ts = s_state[1], pen_ts = s_state[2], has_ts = s_state[3];
   const int bound = s_state[4], tb = r.ts_begin;
 
-  auto masked = [&](int v) -> bool {
-    const unsigned char f = flags[v];
+  auto masked_f = [&](int v, unsigned char f) -> bool {
     if (f & 1) return true;
     if (at_begin && (f & 2)) return true;
     if (return_ts) {
@@ -88,12 +87,26 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
     }
     return false;
   };
+  auto masked = [&](int v) -> bool { return masked_f(v, flags[v]); };
 
   Best bt = {-INFINITY, r.vocab}, bs = {-INFINITY, r.vocab};
-  for (int v = tid; v < r.vocab; v += SM_THREADS) {
-    if (masked(v)) continue;
-    Best c = {row[v], v};
-    if (v < tb) bt = better(bt, c); else bs = better(bs, c);
+  constexpr int U = 8;  // independent loads in flight per thread (the row is 207 KB: latency-, not bandwidth-bound)
+  for (int v0 = tid; v0 < r.vocab; v0 += U * SM_THREADS) {
+    float x[U];
+    unsigned char f[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * SM_THREADS;
+      x[u] = v < r.vocab ? row[v] : -INFINITY;
+      f[u] = v < r.vocab ? flags[v] : (unsigned char)1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = v0 + u * SM_THREADS;
+      if (v >= r.vocab || masked_f(v, f[u])) continue;
+      Best c = {x[u], v};
+      if (v < tb) bt = better(bt, c); else bs = better(bs, c);
+    }
   }
   bt = warp_best(bt);
   bs = warp_best(bs);
