@@ -235,7 +235,8 @@ dec_self_attn_kernel(const float* __restrict__ qkv, T* __restrict__ kc, T* __res
   __shared__ float s_p[512];
   __shared__ float s_red[4];
   __shared__ float s_o[4][HD];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // lets a PDL-launched projection start its prologue
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, sub = lane >> 3, l8 = lane & 7;
   const float* row = qkv + (size_t)b * 3 * d;
@@ -328,8 +329,10 @@ int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d,
                   cudaStream_t st) {
   KW_REQUIRE(pos >= 0 && pos < max_t && max_t <= 512, "dec_self_attn: pos=%d max_t=%d", pos, max_t);
   dim3 grid(H, B);
-  if (t == KW_BF16) dec_self_attn_kernel<bf16><<<grid, 128, 0, st>>>(qkv, (bf16*)kc, (bf16*)vc, (bf16*)out, d, H, max_t, pos);
-  else dec_self_attn_kernel<float><<<grid, 128, 0, st>>>(qkv, (float*)kc, (float*)vc, (float*)out, d, H, max_t, pos);
+  if (t == KW_BF16)
+    KW_CUDA_OK(launch_pdl(dec_self_attn_kernel<bf16>, grid, dim3(128), 0, st, qkv, (bf16*)kc, (bf16*)vc, (bf16*)out, d, H, max_t, pos));
+  else
+    KW_CUDA_OK(launch_pdl(dec_self_attn_kernel<float>, grid, dim3(128), 0, st, qkv, (float*)kc, (float*)vc, (float*)out, d, H, max_t, pos));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;
@@ -349,7 +352,8 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T*
   extern __shared__ float s_p[];  // [S]
   __shared__ float s_red[XA_WARPS];
   __shared__ float s_o[XA_WARPS][HD];
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, sub = lane >> 3, l8 = lane & 7;
   const size_t ld = 2 * (size_t)d;
@@ -451,8 +455,10 @@ int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int
                    cudaStream_t st) {
   dim3 grid(H, B);
   const size_t smem = sizeof(float) * S;
-  if (t == KW_BF16) dec_cross_attn_kernel<bf16><<<grid, XA_THREADS, smem, st>>>(q, (const bf16*)xkv, (bf16*)out, d, S);
-  else dec_cross_attn_kernel<float><<<grid, XA_THREADS, smem, st>>>(q, (const float*)xkv, (float*)out, d, S);
+  if (t == KW_BF16)
+    KW_CUDA_OK(launch_pdl(dec_cross_attn_kernel<bf16>, grid, dim3(XA_THREADS), smem, st, q, (const bf16*)xkv, (bf16*)out, d, S));
+  else
+    KW_CUDA_OK(launch_pdl(dec_cross_attn_kernel<float>, grid, dim3(XA_THREADS), smem, st, q, (const float*)xkv, (float*)out, d, S));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

@@ -68,7 +68,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ bias, T* __restrict__ out, int rows,
                                                         int d) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // lets a PDL-launched projection start its prologue
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -115,6 +116,8 @@ template <typename T>
 __global__ void __launch_bounds__(128) embed_kernel(const int* __restrict__ tokens, int ld_tokens, int pos,
                                                     const T* __restrict__ E, const float* __restrict__ P,
                                                     float* __restrict__ x, int d, int vocab) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   int tok = tokens[(size_t)b * ld_tokens + pos];
   tok = min(max(tok, 0), vocab - 1);
@@ -159,8 +162,8 @@ int im2col_conv2(const void* h0, void* A2, int B, int d, int Tin, int Tout, kw_d
 int layernorm(const float* x, const float* w, const float* b, void* out, int rows, int d, kw_dtype t, cudaStream_t st) {
   KW_REQUIRE(d % 4 == 0 && d <= LN_MAX_VEC * 128, "layernorm: d=%d unsupported", d);
   int blocks = ceil_div(rows, 8);
-  if (t == KW_BF16) layernorm_kernel<bf16><<<blocks, 256, 0, st>>>(x, w, b, (bf16*)out, rows, d);
-  else layernorm_kernel<float><<<blocks, 256, 0, st>>>(x, w, b, (float*)out, rows, d);
+  if (t == KW_BF16) KW_CUDA_OK(launch_pdl(layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, st, x, w, b, (bf16*)out, rows, d));
+  else KW_CUDA_OK(launch_pdl(layernorm_kernel<float>, dim3(blocks), dim3(256), 0, st, x, w, b, (float*)out, rows, d));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;
@@ -168,8 +171,10 @@ int layernorm(const float* x, const float* w, const float* b, void* out, int row
 
 int embed(const int* tokens, int ld_tokens, int pos, const void* E, const float* P, float* x, int B, int d, int vocab,
           kw_dtype t, cudaStream_t st) {
-  if (t == KW_BF16) embed_kernel<bf16><<<B, 128, 0, st>>>(tokens, ld_tokens, pos, (const bf16*)E, P, x, d, vocab);
-  else embed_kernel<float><<<B, 128, 0, st>>>(tokens, ld_tokens, pos, (const float*)E, P, x, d, vocab);
+  if (t == KW_BF16)
+    KW_CUDA_OK(launch_pdl(embed_kernel<bf16>, dim3(B), dim3(128), 0, st, tokens, ld_tokens, pos, (const bf16*)E, P, x, d, vocab));
+  else
+    KW_CUDA_OK(launch_pdl(embed_kernel<float>, dim3(B), dim3(128), 0, st, tokens, ld_tokens, pos, (const float*)E, P, x, d, vocab));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

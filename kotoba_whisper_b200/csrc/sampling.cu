@@ -44,6 +44,8 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
   __shared__ int s_state[5];  // at_begin, last_ts, pen_ts, has_ts, bound
   __shared__ Best s_text[SM_THREADS / 32], s_ts[SM_THREADS / 32];
   __shared__ float s_sum[SM_THREADS / 32];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* row = logits + (size_t)b * r.vocab;
   int* trow = tokens + (size_t)b * ld_tokens;
@@ -147,7 +149,8 @@ int sample_launch(const float* logits, const unsigned char* flags, const SampleR
                   int B, int pos, int begin_index, int return_ts, int* finished, cudaStream_t st) {
   KW_REQUIRE(pos + 1 < ld_tokens && pos + 1 >= begin_index && begin_index >= 1, "sample: pos=%d begin=%d ld=%d", pos,
              begin_index, ld_tokens);
-  sample_kernel<<<B, SM_THREADS, 0, st>>>(logits, flags, r, tokens, ld_tokens, pos, begin_index, return_ts, finished);
+  KW_CUDA_OK(launch_pdl(sample_kernel, dim3(B), dim3(SM_THREADS), 0, st, logits, flags, r, tokens, ld_tokens, pos,
+                        begin_index, return_ts, finished));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

@@ -20,8 +20,10 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int iters) {
   if (warp == 0 && lane == 0) {
     const uint64_t da = make_desc(base), db = make_desc(base + 16384);
     constexpr uint32_t idesc = make_idesc(128, N, 0, 0);
+    mbar_arrive(bar + 24);  // barrier 3: phase 0 completes now, so waiting on parity 0 always succeeds immediately
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
+      if (COMMIT >= 2) { mbar_wait(bar + 24, 0); tc_fence_after(); }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) umma_f16(tmem, da + 2 * kk, db + 2 * kk, idesc, 1);
       if (COMMIT) umma_commit(bar + 8 * (it & 1));
@@ -44,4 +46,4 @@ template <int N, int COMMIT> void run() {
   printf("N=%3d commit/4=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  (err %s)\n", N, COMMIT, (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), cudaGetErrorString(cudaGetLastError()));
   cudaFree(out);
 }
-int main() { run<64, 0>(); run<64, 1>(); run<128, 0>(); run<128, 1>(); run<256, 0>(); run<256, 1>(); return 0; }
+int main() { run<64, 0>(); run<64, 1>(); run<64, 2>(); run<128, 1>(); run<128, 2>(); run<256, 0>(); run<256, 1>(); run<256, 2>(); return 0; }
