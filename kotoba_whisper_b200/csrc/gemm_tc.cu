@@ -606,8 +606,12 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue + weight prefetch overlap the
     attrs[0].val.programmaticStreamSerializationAllowed = 1;           // preceding kernel's tail (PDL)
+    static const int pdl_gemm = [] {
+      const char* e = getenv("KW_PDL_GEMM");
+      return e ? atoi(e) : 1;
+    }();
     cfg.attrs = attrs;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_gemm ? 1 : 0;
     if (R == 32) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<32>, tmB, tmA, p));
     else KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<128>, tmB, tmA, p));
     KW_LAUNCH_OK();
