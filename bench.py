@@ -221,10 +221,12 @@ def ours(args, rank: int, world: int, local_rank: int):
 
     for _ in range(args.warmup):
         step_resident()
-    prof_mask = (1 << _lib.PROF_ENC_GEMM) | (1 << _lib.PROF_ENC_ATTN) | (1 << _lib.PROF_DEC_CROSS) | (1 << _lib.PROF_LOGMEL)
+    # Timed region: only the dominant kernel category (encoder GEMMs) carries CUDA-event pairs; the other categories
+    # are timed the same way in two extra, untimed steps right after (event pairs between the decode kernels would
+    # break the programmatic-dependent-launch overlap the timed region is supposed to measure).
     for c in range(6):
         _lib.profile_read(c, reset=True)
-    lib.kw_profile_enable(prof_mask)
+    lib.kw_profile_enable(1 << _lib.PROF_ENC_GEMM)
     lib.kw_launch_count(1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -232,8 +234,12 @@ def ours(args, rank: int, world: int, local_rank: int):
     ms, ids = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(lib.kw_launch_count(0))
-    prof = {c: _lib.profile_read(c, reset=True) for c in (_lib.PROF_ENC_GEMM, _lib.PROF_ENC_ATTN, _lib.PROF_DEC_CROSS,
-                                                          _lib.PROF_LOGMEL)}
+    prof = {_lib.PROF_ENC_GEMM: _lib.profile_read(_lib.PROF_ENC_GEMM, reset=True)}
+    extra_steps = 2
+    lib.kw_profile_enable((1 << _lib.PROF_ENC_ATTN) | (1 << _lib.PROF_DEC_CROSS) | (1 << _lib.PROF_LOGMEL))
+    ms_extra, _ = timed(step_resident, extra_steps)
+    for c in (_lib.PROF_ENC_ATTN, _lib.PROF_DEC_CROSS, _lib.PROF_LOGMEL):
+        prof[c] = _lib.profile_read(c, reset=True)
     lib.kw_profile_enable(0)
     passes = stats.get("passes", 0)
 
@@ -247,24 +253,24 @@ def ours(args, rank: int, world: int, local_rank: int):
         return
     hbm, tf_sus, tf_burst, peak_src = load_peaks()
 
-    def leg(cat, unit_scale):
+    def leg(cat, unit_scale, total_ms):
         t, n, work = prof[cat]
-        return (work / unit_scale) / (t / 1e3) if t > 0 else 0.0, n, t
+        return (work / unit_scale) / (t / 1e3) if t > 0 else 0.0, n, t / total_ms
 
-    g_tf, g_n, g_ms = leg(_lib.PROF_ENC_GEMM, 1e12)
-    a_tf, a_n, a_ms = leg(_lib.PROF_ENC_ATTN, 1e12)
-    x_gb, x_n, x_ms = leg(_lib.PROF_DEC_CROSS, 1e9)
-    m_gb, m_n, m_ms = leg(_lib.PROF_LOGMEL, 1e9)
+    g_tf, g_n, g_share = leg(_lib.PROF_ENC_GEMM, 1e12, ms)
+    a_tf, a_n, a_share = leg(_lib.PROF_ENC_ATTN, 1e12, ms_extra)
+    x_gb, x_n, x_share = leg(_lib.PROF_DEC_CROSS, 1e9, ms_extra)
+    m_gb, m_n, m_share = leg(_lib.PROF_LOGMEL, 1e9, ms_extra)
     roofline = {"kernel": "encoder GEMMs (conv stem, QKV, out, fc1, fc2)", "bound": "tensor", "achieved": g_tf,
                 "peak": tf_sus, "unit": "TFLOP/s", "frac": g_tf / tf_sus, "traffic": None, "peak_source": peak_src,
-                "launches": g_n, "share_of_step": g_ms / ms}
+                "launches": g_n, "share_of_step": g_share}
     extra = [
         {"kernel": "encoder self-attention", "bound": "tensor", "achieved": a_tf, "peak": tf_sus, "unit": "TFLOP/s",
-         "frac": a_tf / tf_sus, "launches": a_n, "share_of_step": a_ms / ms},
+         "frac": a_tf / tf_sus, "launches": a_n, "share_of_step": a_share},
         {"kernel": "decode-step cross-attention", "bound": "hbm", "achieved": x_gb, "peak": hbm, "unit": "GB/s",
-         "frac": x_gb / hbm, "launches": x_n, "share_of_step": x_ms / ms},
+         "frac": x_gb / hbm, "launches": x_n, "share_of_step": x_share},
         {"kernel": "log-mel (stft+mel+log, incl. fix-up pass)", "bound": "hbm", "achieved": m_gb, "peak": hbm,
-         "unit": "GB/s", "frac": m_gb / hbm, "launches": m_n, "share_of_step": m_ms / ms},
+         "unit": "GB/s", "frac": m_gb / hbm, "launches": m_n, "share_of_step": m_share},
     ]
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -279,7 +285,7 @@ def ours(args, rank: int, world: int, local_rank: int):
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                        "passes_per_step": passes, "l2": "inputs_larger_than_l2 (123 MB audio + 1.5 GB weights per step)",
                        "tokens_out_shape": list(ids.shape)},
-            "roofline": roofline, "roofline_extra": extra, "cpu_baseline": cpu,
+            "roofline": roofline, "roofline_extra": extra, "roofline_extra_note": f"timed with CUDA events in {extra_steps} extra steps after the timed region", "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "audio_s/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(audio_host.nbytes) * world,
                     "d2h_bytes_per_step": int(ids_host.numel() * ids_host.element_size())},

@@ -20,16 +20,18 @@ extern std::atomic<long long> g_launches;
 
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 #ifndef KW_EPI_WARPS
 #define KW_EPI_WARPS 8
 #endif
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int N_EPI_WARPS = KW_EPI_WARPS, THREADS = 32 * (N_EPI_WARPS + 2);  // wide kernels: 16 epilogue warps + TMA + MMA
 constexpr int EPI_THREADS = N_EPI_WARPS * 32, EPI_COLS = BN / (N_EPI_WARPS / 4);  // 64 columns per epilogue warp
 constexpr int SK_EPI_WARPS = 4, SK_THREADS = 32 * (SK_EPI_WARPS + 2);  // skinny kernel
 constexpr int TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + 2 * BN * 4 /*bias*/;
+constexpr int EPI_STAGE_LD = 20, EPI_STAGE_FLOATS = 32 * EPI_STAGE_LD;  // per-warp transpose buffer: 32 rows x 16 cols (+4 pad)
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + 2 * BN * 4 /*bias*/ +
+                              KW_EPI_WARPS * EPI_STAGE_FLOATS * 4 /*residual epilogue staging*/;
 
 struct Params {
   unsigned long long* stamps;  // debug timeline (globaltimer ns) written by CTA 0, or nullptr
@@ -65,20 +67,39 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
 // under the 113-register budget of a 576-thread CTA.  Waits for the accumulator (tfull), then TMEM -> registers -> bias /
 // GELU / residual / position add -> 16-byte global stores.  Shared by the 1-CTA and 2-CTA kernels.
 __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc, int m0, int n0, int quarter, int cgrp,
-                                              int lane, float* s_bias_stage, uint32_t tfull_addr, uint32_t tfull_parity) {
+                                              int lane, float* s_bias_stage, float* s_stage, uint32_t tfull_addr,
+                                              uint32_t tfull_parity) {
   const int row = m0 + quarter * 32 + lane;
   const bool row_ok = row < p.M;
   constexpr int NCH = EPI_COLS / 16;
   const int cbeg = cgrp * NCH;        // chunk index in units of 16 columns
-  float4 xr[4];                       // residual prefetch (EPI_RESID): independent of the MMAs, so issue it early
-  const float* xrow = reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo;
-  auto prefetch_resid = [&](int c) {
+  // EPI_RESID (fp32 residual stream, read-modify-write): one thread per ROW would touch 32 different 128-byte lines per
+  // instruction, which makes the LSU — not the MMAs — the limiter of the K = 1280 out-projection.  The 32 x 16 block is
+  // therefore transposed through a per-warp smem buffer so that half-warps read / add / write 64 contiguous bytes of
+  // one row; the residual for the next chunk is prefetched (independent of the MMAs) before the accumulator wait.
+  const int rsub = lane >> 4, csub = lane & 15;   // coalesced phase: rows 2*it + rsub, column csub
+  float xr[16], xn[16];  // residual of the current chunk / of the next one (loads issued a whole chunk ahead)
+  float* xbase = reinterpret_cast<float*>(p.out) + (size_t)(m0 + quarter * 32) * p.ldo + csub;
+  auto load_resid = [&](int c, float* dst) {
     const int col0 = n0 + c * 16;
-    if (p.epi == EPI_RESID && row_ok && col0 < p.N) {
+    if (p.epi == EPI_RESID && col0 < p.N) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xr[j] = *reinterpret_cast<const float4*>(xrow + col0 + 4 * j);
+      for (int it = 0; it < 16; ++it) {
+        const int rr = 2 * it + rsub;
+        dst[it] = (m0 + quarter * 32 + rr < p.M) ? xbase[(size_t)rr * p.ldo + col0] : 0.0f;
+      }
     }
   };
+  auto prefetch_resid = [&](int c) { load_resid(c, xr); };
+  if (p.epi == EPI_RESID && row_ok) {
+    // pull this warp's residual rows (EPI_COLS fp32 = 2-4 lines per row) towards L2 while the MMAs of this tile still
+    // run: the chunk-by-chunk loads below then pay an L2 hit instead of an HBM round trip each
+    const char* rp = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo + n0 +
+                                                   cgrp * EPI_COLS);
+#pragma unroll
+    for (int j = 0; j < EPI_COLS * 4 / 128; ++j)
+      if (n0 + cgrp * EPI_COLS + j * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * 128));
+  }
   prefetch_resid(cbeg);
   if (threadIdx.x < BN) {  // this tile's 256 bias values -> smem; reads below are conflict-free broadcasts
     const int col = n0 + threadIdx.x;
@@ -92,6 +113,7 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
   for (int c = cbeg; c < cbeg + NCH; ++c) {
     const int col0 = n0 + c * 16;
     if (col0 >= p.N) break;  // warp-uniform
+    if (p.epi == EPI_RESID && c + 1 < cbeg + NCH) load_resid(c + 1, xn);  // in flight during this whole chunk
     uint32_t r[16];
     tmem_ld16(taddr + c * 16, r);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -99,11 +121,23 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
     if (p.epi == EPI_RESID) {
+      const float4* b4p = reinterpret_cast<const float4*>(s_bias_stage + c * 16);
+      __syncwarp();  // previous chunk's coalesced reads of the staging buffer are done
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        v[4 * j] += xr[j].x; v[4 * j + 1] += xr[j].y; v[4 * j + 2] += xr[j].z; v[4 * j + 3] += xr[j].w;
+        const float4 b4 = b4p[j];
+        *reinterpret_cast<float4*>(s_stage + lane * EPI_STAGE_LD + 4 * j) =
+            make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
       }
-      if (c + 1 < cbeg + NCH) prefetch_resid(c + 1);  // next chunk's residual in flight during this chunk's stores
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int rr = 2 * it + rsub;
+        if (m0 + quarter * 32 + rr < p.M) xbase[(size_t)rr * p.ldo + col0] = xr[it] + s_stage[rr * EPI_STAGE_LD + csub];
+      }
+#pragma unroll
+      for (int it = 0; it < 16; ++it) xr[it] = xn[it];
+      continue;
     }
     if (row_ok) {
       {
@@ -238,8 +272,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
       const uint32_t as = tcount & 1;
-      epilogue_tile(p, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN, tfull_bar(as),
-                    (tcount >> 1) & 1);
+      epilogue_tile(p, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN,
+                    s_bias + 2 * BN + warp * EPI_STAGE_FLOATS, tfull_bar(as), (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tempty_bar(as));  // one arrival per epilogue thread hands the accumulator back to the MMA warp
     }
@@ -262,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 namespace c2 {
 constexpr int STAGES = 6;
 constexpr int A_BYTES = 128 * BK * 2, B_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA: 32 KB
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + 2 * BN * 4;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + 2 * BN * 4 + KW_EPI_WARPS * EPI_STAGE_FLOATS * 4;
 constexpr uint32_t IDESC = make_idesc(256, BN, 0, 0);
 }  // namespace c2
 
@@ -354,8 +388,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int t = pair; t < n_tiles; t += n_pairs, ++tcount) {
       const int m0 = (t / tiles_n) * 256 + (int)rank * 128, n0 = (t % tiles_n) * BN;
       const uint32_t as = tcount & 1;
-      epilogue_tile(p, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN, tfull_bar(as),
-                    (tcount >> 1) & 1);
+      epilogue_tile(p, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN,
+                    s_bias + 2 * BN + warp * EPI_STAGE_FLOATS, tfull_bar(as), (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0));  // both CTAs' epilogue threads hand the accumulator back
     }

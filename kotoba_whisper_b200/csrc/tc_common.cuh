@@ -170,8 +170,10 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// .relaxed: the arrival only has to order this thread's TMEM reads (tcgen05.fence::before_thread_sync is issued before
+// it); a .release here would also make every epilogue thread wait for its global stores to drain (ERRBAR / membar stall)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair into its own shared memory; the bytes are credited to the mbarrier at
 // `bar_cluster_addr` (a shared::cluster address, normally the leader CTA's barrier)
