@@ -244,7 +244,25 @@ def ours(args, rank: int, world: int, local_rank: int):
     passes = stats.get("passes", 0)
 
     step_e2e()
-    ms_e2e, ids_host = timed(step_e2e, args.steps)
+    ms_e2e_serial, ids_host = timed(step_e2e, args.steps)
+
+    # Headline e2e: the same public calls with the feature extractor's prefetch handle, the way the reference's
+    # DataLoader workers prepare batch i+1 while the model labels batch i.  Every step's host staging, H2D copy and
+    # D2H token read happen inside the timed region; only their overlap with the previous step's kernels differs.
+    def run_e2e_pipelined(steps):
+        out = None
+        pending = fe.prefetch(clips_host, sampling_rate=SR, return_tensors="pt")
+        for i in range(steps):
+            feats = pending.result()["input_features"]
+            if i + 1 < steps:
+                pending = fe.prefetch(clips_host, sampling_rate=SR, return_tensors="pt")
+            ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False,
+                                 max_length=MAX_LENGTH)
+            out = gather_token_ids(ids, pad).cpu()
+        return out
+
+    run_e2e_pipelined(2)
+    ms_e2e, ids_host = timed(lambda: run_e2e_pipelined(args.steps), 1)
 
     audio_s = BATCH * CLIP_S * world
     value = audio_s * args.steps / (ms / 1e3)
@@ -287,6 +305,9 @@ def ours(args, rank: int, world: int, local_rank: int):
                        "tokens_out_shape": list(ids.shape)},
             "roofline": roofline, "roofline_extra": extra, "roofline_extra_note": f"timed with CUDA events in {extra_steps} extra steps after the timed region", "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "audio_s/s", "ms_per_step": ms_e2e / args.steps,
+                    "mode": "prefetch: step i+1 staged + copied on a side stream while step i runs",
+                    "serial_ms_per_step": ms_e2e_serial / args.steps,
+                    "serial_value": audio_s * args.steps / (ms_e2e_serial / 1e3),
                     "h2d_bytes_per_step": int(audio_host.nbytes) * world,
                     "d2h_bytes_per_step": int(ids_host.numel() * ids_host.element_size())},
             "gpu_launches": launches, "clocks": clocks}

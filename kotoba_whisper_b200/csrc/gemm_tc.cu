@@ -403,41 +403,130 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ---------------------------------------------------------------------------------------------------------------------
 // Decode-time ("skinny") variant: M = batch <= 64 rows of activations against a weight matrix that is read exactly once.
 // The product is computed transposed, out^T[N, M] = W[N,K] . A[M,K]^T, so the 128-row MMA dimension streams weight
-// rows and the batch is the N = 64 dimension: 128 x 64 x K tiles, 8-stage ring (128 KB of weights in flight per SM —
-// this kernel is HBM-bound), two 64-column TMEM accumulators.  Epilogue: thread = output feature, lanes = 32 consecutive
-// features, so each per-batch-row store is a coalesced 128 B (fp32) / 64 B (bf16) segment.
+// rows and the batch is the N = 64 dimension: R x 64 x K tiles, a deep TMA ring (this kernel is bound by how fast one SM
+// can pull bytes, ~50 GB/s per CTA measured), two 64-column TMEM accumulators.
+//
+// Split-K over a thread-block cluster: the d x d and fc2 projections (N = 1280) only make 40 tiles, so their K-loop ran
+// on 40 of 148 SMs.  Launched as clusters of S CTAs, CTA `rank` of a cluster accumulates k-blocks [rank K/S, (rank+1) K/S)
+// of the SAME tile and drops its raw fp32 partial into slot `rank` of the staging buffer of CTA 0 through distributed
+// shared memory; after one cluster barrier CTA 0 adds the S partials in rank order (deterministic: no atomics) and runs
+// the epilogue.
+//
+// Epilogue: the accumulator (lane = output feature, column = batch row) is transposed through the staging buffer so
+// that all four epilogue warps write whole 16-byte groups of one batch row; bias / residual values are requested in that
+// same layout before the accumulator wait.
 namespace sk {
 constexpr int BM = 128, BN = 64;  // MMA shape: 128 weight rows x 64 batch columns
+constexpr int MAX_SPLIT = 4;
 // R = weight rows actually loaded (and produced) per tile.  R = 32 quarters the bytes per stage, so small-N projections
-// spread over 4x more CTAs and a 16-stage ring holds a whole K = 1280 slice in ~one round trip; the MMA still runs at
-// M = 128 and simply reads stale shared memory for rows R..127, whose accumulator rows are never read back.
+// spread over 4x more CTAs; the MMA still runs at M = 128 and simply reads stale shared memory for rows R..127, whose
+// accumulator rows are never read back.
 template <int R> struct Cfg {
   static constexpr int A_BYTES = R * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = R == 32 ? 16 : 8;
+  static constexpr int STAGES = R == 32 ? 12 : 8;
+  // k-block slots that share one full / empty mbarrier pair (one wait + fence per group on the MMA-issuing thread)
+  static constexpr int GROUP = R == 32 ? 4 : 2;
   static constexpr int RING = STAGES * STAGE_BYTES + (BM - R) * BK * 2;  // + tail the M = 128 read of the last stage may touch
-  static constexpr size_t SMEM_BYTES = 1024 + (size_t)RING + 512;
+  static constexpr int SLOTS = R == 32 ? MAX_SPLIT : 1;                  // split-K partial slots (R = 32 only)
+  static constexpr int OUT_STAGE = SLOTS * BN * R * 4;                   // [slot][batch row][feature] fp32
+  static constexpr size_t SMEM_BYTES = 1024 + (size_t)RING + 512 + OUT_STAGE;
 };
+static_assert(Cfg<32>::SMEM_BYTES <= 232448 && Cfg<128>::SMEM_BYTES <= 232448, "skinny GEMM smem budget");
 constexpr int TMEM_COLS = 128;
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
 }  // namespace sk
 
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+// Coalesced half of the skinny epilogue for one tile: V consecutive features of one batch row per item, items spread
+// over the 128 epilogue threads.  `stage` = [n_slots][64][R] fp32 partial sums, `res` = residual values preloaded in the
+// same item order (EPI_RESID, V = 4 only).
+template <int R, int V, int EPI, bool OUT_BF16>
+__device__ __forceinline__ void skinny_store(const Params& p, const float* stage, int n_slots, int n0, int tid,
+                                             const float4* res) {
+  constexpr int GROUPS = R / V, ITEMS = sk::BN * GROUPS, PER = ITEMS / (SK_EPI_WARPS * 32);
+  constexpr int UNROLL = PER <= 4 ? PER : 4;  // res[i] (PER = 4) needs the full unroll; longer loops keep registers down
+#pragma unroll UNROLL
+  for (int i = 0; i < PER; ++i) {
+    const int idx = tid + i * SK_EPI_WARPS * 32, row = idx / GROUPS, f = (idx % GROUPS) * V, n = n0 + f;
+    if (row >= p.M || n >= p.N) continue;
+    float v[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = stage[row * R + f + e];
+    for (int sl = 1; sl < n_slots; ++sl) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] += stage[(sl * sk::BN + row) * R + f + e];
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] += __ldg(p.bias + n + e);
+    }
+    if (EPI == EPI_GELU) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[e] = OUT_BF16 ? gelu_fast(v[e]) : gelu_erf(v[e]);
+    }
+    if (OUT_BF16) {
+      bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + n;
+      if (V == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+      else if (V == 2) *reinterpret_cast<uint32_t*>(o) = pack_bf16(v[0], v[V - 1]);
+      else o[0] = __float2bfloat16_rn(v[0]);
+    } else {
+      float* o = reinterpret_cast<float*>(p.out) + (size_t)row * p.ldo + n;
+      if (EPI == EPI_RESID) {
+        if (V == 4 && R == 32) { v[0] += res[i].x; v[1] += res[i].y; v[V - 2] += res[i].z; v[V - 1] += res[i].w; }
+        else {
+#pragma unroll
+          for (int e = 0; e < V; ++e) v[e] += o[e];
+        }
+      }
+      if (V == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[V - 2], v[V - 1]);
+      else if (V == 2) *reinterpret_cast<float2*>(o) = make_float2(v[0], v[V - 1]);
+      else o[0] = v[0];
+    }
+  }
+}
+
+template <int R, int V>
+__device__ __forceinline__ void skinny_store_dispatch(const Params& p, const float* stage, int n_slots, int n0, int tid,
+                                                      const float4* res) {
+  if (p.out_bf16) {
+    if (p.epi == EPI_GELU) skinny_store<R, V, EPI_GELU, true>(p, stage, n_slots, n0, tid, res);
+    else skinny_store<R, V, EPI_STORE, true>(p, stage, n_slots, n0, tid, res);
+  } else {
+    if (p.epi == EPI_GELU) skinny_store<R, V, EPI_GELU, false>(p, stage, n_slots, n0, tid, res);
+    else if (p.epi == EPI_RESID) skinny_store<R, V, EPI_RESID, false>(p, stage, n_slots, n0, tid, res);
+    else skinny_store<R, V, EPI_STORE, false>(p, stage, n_slots, n0, tid, res);
+  }
+}
+
 template <int R>
 __global__ void __launch_bounds__(SK_THREADS, 1)
-gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params p) {
+gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params p,
+                      const int vec) {
   using C = sk::Cfg<R>;
   constexpr int BM = R, BN = sk::BN, STAGES = C::STAGES, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int GROUP = C::GROUP;  // barrier g serves slots [g*GROUP, (g+1)*GROUP)
   constexpr int TMEM_COLS = sk::TMEM_COLS;
   constexpr uint32_t IDESC = sk::IDESC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar0 = base + C::RING;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
-  uint32_t* tmem_slot_ptr =
-      reinterpret_cast<uint32_t*>(smem_raw + (base - smem_u32(smem_raw)) + C::RING + 8 * (2 * STAGES + 4));
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + C::RING + 8 * (2 * STAGES + 4));
+  float* out_stage = reinterpret_cast<float*>(gen_base + C::RING + 512);  // [slot][64][R]
+  const uint32_t out_stage_u32 = base + C::RING + 512;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   auto stamp = [&](int i) {
@@ -449,8 +538,13 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   };
   if (threadIdx.x == 0) stamp(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // split-K: the S CTAs of a cluster share one tile
+  const int S = R == 32 ? (int)cluster_nctarank() : 1, rank = R == 32 ? (int)cluster_ctarank() : 0;
   const int n_tiles = (p.N + BM - 1) / BM;  // tiles over output features
-  const int k_blocks = p.K / BK;
+  const int n_workers = (int)gridDim.x / S, worker = (int)blockIdx.x / S;
+  const int kb_all = p.K / BK;
+  const int kb_begin = rank * kb_all / S, k_blocks = (rank + 1) * kb_all / S - kb_begin;  // this CTA's k-range
+  const int my_tiles = (n_tiles - worker + n_workers - 1) / n_workers;
 
   if (warp == 4 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -470,52 +564,64 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // split-K handshake #1: every CTA of the cluster is running before anyone stores into CTA 0's shared memory (the
+  // matching wait sits right before those stores, long after the arrival — it never stalls)
+  if (R == 32 && S > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
   if (warp == 4) {
     if (lane == 0) {
-      const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const uint32_t total = (uint32_t)my_tiles * k_blocks;
-      auto tile_of = [&](uint32_t it) { return (int)blockIdx.x + (int)(it / k_blocks) * (int)gridDim.x; };
+      auto tile_of = [&](uint32_t it) { return worker + (int)(it / k_blocks) * n_workers; };
+      auto kcoord = [&](uint32_t it) { return (kb_begin + (int)(it % k_blocks)) * BK; };
       // Programmatic dependent launch: weights do not depend on the preceding kernel, so the first ring of weight
       // tiles is requested before griddepcontrol.wait; only the activation tiles wait for the producer grid.
       const uint32_t pre = total < (uint32_t)STAGES ? total : (uint32_t)STAGES;
+      auto group_bytes = [&](uint32_t it0) {  // bytes of the barrier group that starts at k-block it0
+        const uint32_t n = total - it0 < (uint32_t)GROUP ? total - it0 : (uint32_t)GROUP;
+        return n * (uint32_t)STAGE_BYTES;
+      };
       for (uint32_t it = 0; it < pre; ++it) {
-        mbar_expect_tx(full_bar(it), STAGE_BYTES);
-        tma_load_2d(base + it * STAGE_BYTES, &tmW, full_bar(it), (it % k_blocks) * BK, tile_of(it) * BM);
+        const int g = (int)it / GROUP;
+        if (it % GROUP == 0) mbar_expect_tx(full_bar(g), group_bytes(it));
+        tma_load_2d(base + it * STAGE_BYTES, &tmW, full_bar(g), kcoord(it), tile_of(it) * BM);
       }
       stamp(1);
       asm volatile("griddepcontrol.wait;" ::: "memory");
       stamp(2);
       for (uint32_t it = 0; it < pre; ++it)
-        tma_load_2d(base + it * STAGE_BYTES + A_BYTES, &tmA, full_bar(it), (it % k_blocks) * BK, 0);
+        tma_load_2d(base + it * STAGE_BYTES + A_BYTES, &tmA, full_bar((int)it / GROUP), kcoord(it), 0);
       for (uint32_t it = pre; it < total; ++it) {
-        const int s = it % STAGES;
-        mbar_wait(empty_bar(s), ((it / STAGES) & 1) ^ 1);
-        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const int s = it % STAGES, g = s / GROUP;
+        if (it % GROUP == 0) {
+          mbar_wait(empty_bar(g), ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(full_bar(g), group_bytes(it));
+        }
         const uint32_t sa = base + s * STAGE_BYTES;
-        tma_load_2d(sa, &tmW, full_bar(s), (it % k_blocks) * BK, tile_of(it) * BM);
-        tma_load_2d(sa + A_BYTES, &tmA, full_bar(s), (it % k_blocks) * BK, 0);
+        tma_load_2d(sa, &tmW, full_bar(g), kcoord(it), tile_of(it) * BM);
+        tma_load_2d(sa + A_BYTES, &tmA, full_bar(g), kcoord(it), 0);
       }
     }
   } else if (warp == 5) {
     if (lane == 0) {
-      uint32_t it = 0, tcount = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+      uint32_t it = 0;
+      const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)k_blocks;
+      for (uint32_t tcount = 0; tcount < (uint32_t)my_tiles; ++tcount) {
         const uint32_t as = tcount & 1;
         mbar_wait(tempty_bar(as), ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
         for (int kb = 0; kb < k_blocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(full_bar(s), (it / STAGES) & 1);
-          if (it == 0) stamp(3);
-          if (it < 40) stamp(16 + it);
-          tc_fence_after();
+          const int s = it % STAGES, g = s / GROUP;
+          if (it % GROUP == 0) {
+            mbar_wait(full_bar(g), (it / STAGES) & 1);
+            if (it == 0) stamp(3);
+            tc_fence_after();
+          }
           const uint32_t sa = base + s * STAGE_BYTES;
           const uint64_t da = make_desc(sa), db = make_desc(sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0);
-          umma_commit(empty_bar(s));
+          if (it % GROUP == GROUP - 1 || it + 1 == total_it) umma_commit(empty_bar(g));  // group consumed
         }
         umma_commit(tfull_bar(as));
         stamp(4);
@@ -523,59 +629,78 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     }
   } else {
     asm volatile("griddepcontrol.wait;" ::: "memory");  // outputs / residual belong to the preceding kernels
-    uint32_t tcount = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
+    const int tid = threadIdx.x;                  // 0..127
+    const bool row_warp = warp * 32 < R;          // TMEM lanes R..127 hold garbage rows
+    // slot `rank` of the staging buffer of the cluster's CTA 0 (this CTA's own buffer when there is no split)
+    const uint32_t my_slot = out_stage_u32 + (uint32_t)rank * (BN * R * 4);
+    const uint32_t slot_remote = S > 1 ? mapa_u32(my_slot, 0) : 0u;
+    for (int tcount = 0; tcount < my_tiles; ++tcount) {
+      const int t = worker + tcount * n_workers;
       const uint32_t as = tcount & 1;
-      const bool row_warp = warp * 32 < R;        // TMEM lanes R..127 hold garbage rows
-      const int n = t * BM + warp * 32 + lane;    // output feature owned by this thread
-      const bool n_ok = row_warp && n < p.N;
-      const float bias = (p.bias && n_ok) ? __ldg(p.bias + n) : 0.0f;  // in flight while the MMAs finish
+      // EPI_RESID: this thread's residual groups are requested before the accumulator wait (R = 32: 4 x 16 bytes)
+      float4 res[R == 32 ? 4 : 1];
+      if (R == 32 && p.epi == EPI_RESID && vec == 4 && rank == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = tid + i * 128, row = idx / 8, n = t * BM + (idx % 8) * 4;
+          res[i] = (row < p.M && n < p.N)
+                       ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo + n)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
       mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
       if (threadIdx.x == 0 && tcount == 0) stamp(8);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (c * 32 >= p.M || !row_warp) break;  // warp-uniform: no batch rows in this half / no valid weight rows
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (n_ok) {
-          const int nrow = min(32, p.M - c * 32);  // batch rows held in this chunk
-          if (p.out_bf16) {
-            bf16* ob = reinterpret_cast<bf16*>(p.out) + (size_t)(c * 32) * p.ldo + n;
+      if (S > 1) asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // handshake #1
+      if (row_warp) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nrow) {
-                float v = __uint_as_float(r[j]) + bias;
-                if (p.epi == EPI_GELU) v = gelu_fast(v);
-                ob[(size_t)j * p.ldo] = __float2bfloat16_rn(v);
-              }
-            }
+        for (int c = 0; c < BN / 32; ++c) {
+          if (c * 32 >= p.M) break;  // warp-uniform: no batch rows in this half
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int col = warp * 32 + lane;  // feature inside the tile
+          if (S > 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) st_cluster_f32(slot_remote + ((c * 32 + j) * R + col) * 4, __uint_as_float(r[j]));
           } else {
-            float* of = reinterpret_cast<float*>(p.out) + (size_t)(c * 32) * p.ldo + n;
-            float x[32];
-            if (p.epi == EPI_RESID) {  // all residual loads first (independent), then add + store
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = (j < nrow) ? of[(size_t)j * p.ldo] : 0.0f;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nrow) {
-                float v = __uint_as_float(r[j]) + bias;
-                if (p.epi == EPI_GELU) v = gelu_erf(v);
-                if (p.epi == EPI_RESID) v += x[j];
-                of[(size_t)j * p.ldo] = v;
-              }
-            }
+            for (int j = 0; j < 32; ++j) out_stage[(c * 32 + j) * R + col] = __uint_as_float(r[j]);
           }
         }
       }
+      if (threadIdx.x == 0 && tcount == 0) stamp(9);
       tc_fence_before();
       mbar_arrive(tempty_bar(as));
-      if (threadIdx.x == 0) { stamp(5 + (tcount == 0 ? 0 : 1)); }
+      if (S == 1) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer complete
+        if (vec == 4) skinny_store_dispatch<R, 4>(p, out_stage, 1, t * BM, tid, res);
+        else if (vec == 2) skinny_store_dispatch<R, 2>(p, out_stage, 1, t * BM, tid, res);
+        else skinny_store_dispatch<R, 1>(p, out_stage, 1, t * BM, tid, res);
+        if (tcount + 1 < my_tiles) asm volatile("bar.sync 1, 128;" ::: "memory");  // buffer free for the next tile
+        if (threadIdx.x == 0) stamp(5 + (tcount == 0 ? 0 : 1));
+      } else {
+        // split-K (one tile per cluster): every CTA's partial lands in CTA 0, which finishes the tile
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        if (rank == 0) {
+          asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+          if (threadIdx.x == 0) stamp(10);
+          if (vec == 4) skinny_store_dispatch<R, 4>(p, out_stage, S, t * BM, tid, res);
+          else if (vec == 2) skinny_store_dispatch<R, 2>(p, out_stage, S, t * BM, tid, res);
+          else skinny_store_dispatch<R, 1>(p, out_stage, S, t * BM, tid, res);
+          if (threadIdx.x == 0) stamp(5);
+        }
+      }
     }
   }
+  if (R == 32 && S > 1 && warp >= 4) {
+    // the TMA / MMA warps take part in the cluster barrier too (it counts every thread of every CTA)
+    __syncwarp();
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");  // handshake #1
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  }
+  if (R == 32 && S > 1 && !(rank == 0 && warp < 4)) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) stamp(7);
@@ -631,23 +756,48 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     if (rc) return rc;
     if ((rc = make_map(&tmA, g.A, g.M, g.K, g.lda, sk::BN))) return rc;
     const int tiles = ceil_div(g.N, R);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(std::min(tiles, n_sm));
-    cfg.blockDim = dim3(SK_THREADS);
-    cfg.dynamicSmemBytes = R == 32 ? sk::Cfg<32>::SMEM_BYTES : sk::Cfg<128>::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attrs[1];
-    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue + weight prefetch overlap the
-    attrs[0].val.programmaticStreamSerializationAllowed = 1;           // preceding kernel's tail (PDL)
     static const int pdl_gemm = [] {
       const char* e = getenv("KW_PDL_GEMM");
       return e ? atoi(e) : 1;
     }();
+    static const int max_split = [] {  // KW_SPLITK=1 turns the cluster split-K off (A/B measurements)
+      const char* e = getenv("KW_SPLITK");
+      return e ? std::max(1, std::min(atoi(e), sk::MAX_SPLIT)) : 3;
+    }();
+    // split-K over a cluster when the tiles alone leave most SMs idle (N = 1280 projections: 40 tiles -> 120 CTAs)
+    int split = 1;
+    if (R == 32)
+      for (int s2 = max_split; s2 > 1; --s2)
+        if (tiles * s2 <= n_sm && g.K / BK >= 4 * s2) { split = s2; break; }
+    // widest store the output layout allows: V features of one batch row per 16 / 8 / 4-byte (fp32) store
+    const int esz = g.out_type == KW_BF16 ? 2 : 4;
+    int vec = 1;
+    if (g.N % 4 == 0 && g.ldo % 4 == 0 && ((uintptr_t)g.out % (4 * esz)) == 0) vec = 4;
+    else if (g.N % 2 == 0 && g.ldo % 2 == 0 && ((uintptr_t)g.out % (2 * esz)) == 0) vec = 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(split > 1 ? tiles * split : std::min(tiles, n_sm));
+    cfg.blockDim = dim3(SK_THREADS);
+    cfg.dynamicSmemBytes = R == 32 ? sk::Cfg<32>::SMEM_BYTES : sk::Cfg<128>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    if (pdl_gemm) {  // prologue + weight prefetch overlap the preceding kernel's tail (PDL)
+      attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attrs[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (split > 1) {
+      attrs[na].id = cudaLaunchAttributeClusterDimension;
+      attrs[na].val.clusterDim.x = split;
+      attrs[na].val.clusterDim.y = 1;
+      attrs[na].val.clusterDim.z = 1;
+      ++na;
+    }
     cfg.attrs = attrs;
-    cfg.numAttrs = pdl_gemm ? 1 : 0;
-    if (R == 32) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<32>, tmB, tmA, p));
-    else KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<128>, tmB, tmA, p));
+    cfg.numAttrs = na;
+    if (R == 32) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<32>, tmB, tmA, p, vec));
+    else KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<128>, tmB, tmA, p, vec));
     KW_LAUNCH_OK();
     ++g_launches;
     return KW_OK;

@@ -47,6 +47,22 @@ def _convert(value, return_tensors):
     raise ValueError(f"return_tensors={return_tensors!r} is not supported (use None, 'np' or 'pt')")
 
 
+class PendingFeatures:
+    """Handle returned by `WhisperFeatureExtractorB200.prefetch`."""
+
+    def __init__(self, future, device):
+        self._future, self._device = future, device
+
+    def result(self) -> BatchFeature:
+        out, ev = self._future.result()
+        cur = torch.cuda.current_stream(self._device)
+        cur.wait_event(ev)  # device-side wait only: the host does not block on the copy
+        for v in out.values():
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                v.record_stream(cur)
+        return out
+
+
 class WhisperFeatureExtractorB200:
     model_input_names = ["input_features"]
 
@@ -69,8 +85,9 @@ class WhisperFeatureExtractorB200:
         self.nb_max_frames = self.n_samples // hop_length
         self.padding_side = "right"
         self.device = torch.device(device)
-        self._pinned: Optional[torch.Tensor] = None
-        self._copy_done: Optional[torch.cuda.Event] = None
+        self._pinned: List[Optional[torch.Tensor]] = [None, None]
+        self._copy_done: List[Optional[torch.cuda.Event]] = [None, None]
+        self._side: Optional[torch.cuda.Stream] = None
 
     # ---- device entry: already-padded clips on the GPU ---------------------------------------------------------
     def logmel_device(self, audio: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -91,6 +108,63 @@ class WhisperFeatureExtractorB200:
             _lib.check(lib.kw_logmel(audio.data_ptr(), lens_ptr, B, n, self.feature_size, out.data_ptr(),
                                      clip_max.data_ptr(), st), "kw_logmel")
         return out
+
+    # ---- host staging: clips -> pinned buffer -> device, chunk by chunk ------------------------------------------------
+    def _stage_and_copy(self, clips, lens, target: int, dev: torch.device) -> torch.Tensor:
+        """Pad/truncate the clips into a pinned staging buffer and copy them to `dev` on the current stream.  The batch
+        moves in chunks of 8 clips: the H2D copy of chunk i runs while the thread pool stages chunk i+1, so the cost is
+        max(staging, PCIe) instead of their sum.  Two staging buffers alternate, so a `prefetch` for the next batch
+        can fill one while the previous batch's copy is still draining the other."""
+        B = len(clips)
+        slot = self._slot = (getattr(self, "_slot", 1) + 1) % 2
+        if self._pinned[slot] is None or self._pinned[slot].numel() < B * target:
+            self._pinned[slot] = torch.empty(B * target, dtype=torch.float32).pin_memory()
+        if self._copy_done[slot] is not None:
+            self._copy_done[slot].synchronize()  # the copy that last read this staging buffer has drained it
+        host = self._pinned[slot][: B * target].view(B, target)
+        host_np = host.numpy()
+        audio = torch.empty((B, target), dtype=torch.float32, device=dev)
+
+        def stage(i):
+            host_np[i, : lens[i]] = clips[i][: lens[i]]
+            host_np[i, lens[i]:] = self.padding_value
+
+        CH = 8
+        if B >= 2 * CH:  # numpy releases the GIL inside the row copies: 8 rows of 1.9 MB stage in parallel
+            pool = _staging_pool()
+            for c0 in range(0, B, CH):
+                c1 = min(B, c0 + CH)
+                list(pool.map(stage, range(c0, c1)))
+                audio[c0:c1].copy_(host[c0:c1], non_blocking=True)
+        else:
+            for i in range(B):
+                stage(i)
+            audio.copy_(host, non_blocking=True)
+        self._copy_done[slot] = torch.cuda.Event()
+        self._copy_done[slot].record(torch.cuda.current_stream(dev))
+        return audio
+
+    def prefetch(self, raw_speech, **kwargs) -> "PendingFeatures":
+        """Start `__call__(raw_speech, keep_on_device=True, **kwargs)` in the background — host staging on a worker thread,
+        H2D copy and the log-mel kernel on a side stream — and return a handle whose `.result()` hands the features to
+        the caller's current stream.  This is the data-loader prefetch of the reference's labelling loop
+        (run_pseudo_labelling.py:283-296: DataLoader workers prepare batch i+1 while the model runs batch i)."""
+        dev = self.device if kwargs.get("device") in (None, "cpu") else torch.device(kwargs["device"])
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+            from concurrent.futures import ThreadPoolExecutor
+            self._prefetcher = ThreadPoolExecutor(max_workers=1)
+        kwargs["keep_on_device"] = True
+
+        def work():
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(self._side):
+                out = self(raw_speech, **kwargs)
+                ev = torch.cuda.Event()
+                ev.record(self._side)
+            return out, ev
+
+        return PendingFeatures(self._prefetcher.submit(work), dev)
 
     # ---- reference call surface ------------------------------------------------------------------------------------
     def __call__(self, raw_speech, truncation: bool = True, pad_to_multiple_of: Optional[int] = None,
@@ -135,27 +209,8 @@ class WhisperFeatureExtractorB200:
         lens = [min(l, target) for l in lens]
         B = len(clips)
 
-        # stage through one pinned buffer -> one H2D copy
-        if self._pinned is None or self._pinned.numel() < B * target:
-            self._pinned = torch.empty(B * target, dtype=torch.float32).pin_memory()
-        if self._copy_done is not None:
-            self._copy_done.synchronize()  # the previous call's async H2D copy has drained the staging buffer
-        host = self._pinned[: B * target].view(B, target)
-        host_np = host.numpy()
-
-        def stage(i):
-            host_np[i, : lens[i]] = clips[i][: lens[i]]
-            host_np[i, lens[i]:] = self.padding_value
-
-        if B >= 8:  # numpy releases the GIL inside the row copies: staging 64 x 1.9 MB drops from ~10 ms to ~3 ms
-            list(_staging_pool().map(stage, range(B)))
-        else:
-            for i in range(B):
-                stage(i)
         dev = self.device if device in (None, "cpu") else torch.device(device)
-        audio = host.to(dev, non_blocking=True)
-        self._copy_done = torch.cuda.Event()
-        self._copy_done.record(torch.cuda.current_stream(dev))
+        audio = self._stage_and_copy(clips, lens, target, dev)
         lens_t = torch.tensor(lens, dtype=torch.int32)
         if do_normalize:  # zero-mean / unit-variance over the valid samples (feature_extraction_whisper.py:166-187)
             mask = torch.arange(target, device=dev)[None, :] < lens_t.to(dev)[:, None]

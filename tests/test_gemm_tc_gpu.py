@@ -25,7 +25,9 @@ SHAPES = [(128, 256, 64), (256, 512, 128), (100, 128, 128), (1500, 1280, 1280), 
           (3000, 1280, 3840), (1500, 5120, 1280), (1500, 1280, 5120), (333, 192, 576), (4 * 1500, 2560, 1280),
           # decode-time (skinny, transposed-product kernel): M = batch <= 64, any N
           (64, 3840, 1280), (64, 1280, 5120), (4, 51866, 1280), (1, 1280, 1280), (33, 5120, 1280), (64, 128, 128),
-          (17, 200, 64)]
+          (17, 200, 64),
+          # cluster split-K (N <= ~1500: tiles x split <= 148 CTAs): uneven k-ranges, 2- and 3-way, 8 / 4-byte store paths
+          (64, 1280, 1280), (5, 1000, 832), (7, 1282, 512), (3, 333, 1280), (40, 1536, 1024)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
@@ -50,6 +52,18 @@ def test_gemm_tc_matches_torch(M, N, K):
     # same answer as the SIMT kernel (the exact-fp32-accumulation reference path)
     s32 = _run(A, W, b, 0, F32, impl=1)
     assert (o32 - s32).abs().max().item() <= 3e-5 * scale
+
+
+def test_skinny_split_k_is_deterministic():
+    """The split-K partials are added in rank order by one CTA (no atomics): repeated launches give identical bits."""
+    torch.manual_seed(5)
+    A = torch.randn(64, 5120, device="cuda").bfloat16()
+    W = (torch.randn(1280, 5120, device="cuda") * 0.05).bfloat16()
+    b = torch.randn(1280, device="cuda")
+    x0 = torch.randn(64, 1280, device="cuda")
+    first = _run(A, W, b, 2, F32, out=x0.clone())
+    for _ in range(5):
+        assert torch.equal(_run(A, W, b, 2, F32, out=x0.clone()), first)
 
 
 def test_gemm_tc_full_batch_shape_linearity():

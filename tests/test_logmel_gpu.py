@@ -86,3 +86,19 @@ def test_logmel_batch64_properties(fes):
     assert bool(((x >= mx - 2.0 - 1e-6)).all())  # (max(v, clipmax-8)+4)/4 spans at most 2.0
     ref = logmel_f64(cl[40], 128)
     assert np.abs(x[40].cpu().numpy() - ref).max() <= TOL
+
+
+def test_prefetch_matches_blocking_call(fes):
+    """`prefetch` (worker-thread staging, side-stream copy + kernel) hands back the same bits as the blocking call,
+    also when two prefetches are in flight back to back (the two staging buffers alternate)."""
+    fe = fes[128]
+    a = [clip("UGS"[i % 3], 9100 + i) for i in range(24)]       # ragged lengths, chunked staging path (B >= 16)
+    b = [clip("SGU"[i % 3], 9200 + i) for i in range(5)]        # small-batch path
+    want_a = fe(a, sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"].clone()
+    want_b = fe(b, sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"].clone()
+    pa = fe.prefetch(a, sampling_rate=16000, return_tensors="pt")
+    pb = fe.prefetch(b, sampling_rate=16000, return_tensors="pt")
+    pa2 = fe.prefetch(a, sampling_rate=16000, return_tensors="pt")
+    got_a, got_b, got_a2 = pa.result()["input_features"], pb.result()["input_features"], pa2.result()["input_features"]
+    torch.cuda.synchronize()
+    assert torch.equal(got_a, want_a) and torch.equal(got_b, want_b) and torch.equal(got_a2, want_a)

@@ -6,7 +6,7 @@ from kotoba_whisper_b200 import _lib
 lib = _lib.load()
 F32, BF16 = _lib.KW_F32, _lib.KW_BF16
 st = lambda: torch.cuda.current_stream().cuda_stream
-names = {0: "start", 1: "W requested", 2: "dep wait done", 3: "stage0 landed", 4: "last MMA commit", 8: "acc visible", 5: "epilogue done", 7: "all done"}
+names = {0: "start", 1: "W requested", 2: "dep wait done", 3: "stage0 landed", 4: "last MMA commit", 8: "acc visible", 9: "staged", 10: "cluster barrier", 5: "epilogue done", 7: "all done"}
 for (N, K, epi, tag) in [(1280, 1280, 0, "d x d store"), (1280, 1280, 2, "d x d resid"), (1280, 5120, 2, "fc2 resid"), (3840, 1280, 0, "qkv")]:
     A = torch.randn(64, K, device="cuda").bfloat16(); W = (torch.randn(N, K, device="cuda") * 0.02).bfloat16()
     bias = torch.randn(N, device="cuda"); out = torch.zeros(64, N, device="cuda")
