@@ -75,32 +75,36 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
   const int cbeg = cgrp * NCH;        // chunk index in units of 16 columns
   // EPI_RESID (fp32 residual stream, read-modify-write): one thread per ROW would touch 32 different 128-byte lines per
   // instruction, which makes the LSU — not the MMAs — the limiter of the K = 1280 out-projection.  The 32 x 16 block is
-  // therefore transposed through a per-warp smem buffer so that half-warps read / add / write 64 contiguous bytes of
-  // one row; the residual for the next chunk is prefetched (independent of the MMAs) before the accumulator wait.
-  const int rsub = lane >> 4, csub = lane & 15;   // coalesced phase: rows 2*it + rsub, column csub
-  float xr[16], xn[16];  // residual of the current chunk / of the next one (loads issued a whole chunk ahead)
+  // therefore transposed through a per-warp smem buffer so that groups of 4 lanes read / add / write the 64 contiguous
+  // bytes one row owns in this chunk with 16-byte accesses (8 rows per instruction).  The residual of ALL of this
+  // warp's chunks is requested before the accumulator wait: the epilogue warps would otherwise sit idle there, and with
+  // one chunk in flight per warp the HBM / L2 latency (not bandwidth) set the epilogue time.
+  const int rsub = lane >> 2, csub = (lane & 3) * 4;   // coalesced phase: rows 8*it + rsub, columns csub .. csub+3
+  constexpr int XDEPTH = 2;  // chunks of residual in flight per warp (register budget: 168 with 10 warps per CTA)
+  float4 xr[XDEPTH][4];
   float* xbase = reinterpret_cast<float*>(p.out) + (size_t)(m0 + quarter * 32) * p.ldo + csub;
-  auto load_resid = [&](int c, float* dst) {
-    const int col0 = n0 + c * 16;
-    if (p.epi == EPI_RESID && col0 < p.N) {
+  auto load_resid = [&](int cc, float4* dst) {
+    const int col0 = n0 + (cbeg + cc) * 16;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int rr = 2 * it + rsub;
-        dst[it] = (m0 + quarter * 32 + rr < p.M) ? xbase[(size_t)rr * p.ldo + col0] : 0.0f;
-      }
+    for (int it = 0; it < 4; ++it) {
+      const int rr = 8 * it + rsub;
+      dst[it] = (col0 < p.N && m0 + quarter * 32 + rr < p.M)
+                    ? *reinterpret_cast<const float4*>(xbase + (size_t)rr * p.ldo + col0)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  auto prefetch_resid = [&](int c) { load_resid(c, xr); };
-  if (p.epi == EPI_RESID && row_ok) {
-    // pull this warp's residual rows (EPI_COLS fp32 = 2-4 lines per row) towards L2 while the MMAs of this tile still
-    // run: the chunk-by-chunk loads below then pay an L2 hit instead of an HBM round trip each
-    const char* rp = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo + n0 +
-                                                   cgrp * EPI_COLS);
+  if (p.epi == EPI_RESID) {
+    if (row_ok) {
+      // the chunks that are not register-prefetched are at least pulled into L2 while the MMAs of this tile still run
+      const char* rp = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo + n0 +
+                                                     cgrp * EPI_COLS);
 #pragma unroll
-    for (int j = 0; j < EPI_COLS * 4 / 128; ++j)
-      if (n0 + cgrp * EPI_COLS + j * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * 128));
+      for (int j = XDEPTH * 64 / 128; j < EPI_COLS * 4 / 128; ++j)
+        if (n0 + cgrp * EPI_COLS + j * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * 128));
+    }
+#pragma unroll
+    for (int cc = 0; cc < XDEPTH; ++cc) load_resid(cc, xr[cc]);
   }
-  prefetch_resid(cbeg);
   if (threadIdx.x < BN) {  // this tile's 256 bias values -> smem; reads below are conflict-free broadcasts
     const int col = n0 + threadIdx.x;
     s_bias_stage[threadIdx.x] = (p.bias && col < p.N) ? __ldg(p.bias + col) : 0.0f;
@@ -109,11 +113,11 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
   mbar_wait(tfull_addr, tfull_parity);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-  for (int c = cbeg; c < cbeg + NCH; ++c) {
+#pragma unroll
+  for (int cc = 0; cc < NCH; ++cc) {  // unrolled: xr[cc] must stay in registers
+    const int c = cbeg + cc;
     const int col0 = n0 + c * 16;
     if (col0 >= p.N) break;  // warp-uniform
-    if (p.epi == EPI_RESID && c + 1 < cbeg + NCH) load_resid(c + 1, xn);  // in flight during this whole chunk
     uint32_t r[16];
     tmem_ld16(taddr + c * 16, r);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -131,12 +135,16 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
       }
       __syncwarp();
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int rr = 2 * it + rsub;
-        if (m0 + quarter * 32 + rr < p.M) xbase[(size_t)rr * p.ldo + col0] = xr[it] + s_stage[rr * EPI_STAGE_LD + csub];
+      for (int it = 0; it < 4; ++it) {
+        const int rr = 8 * it + rsub;
+        if (m0 + quarter * 32 + rr < p.M) {
+          const float4 a4 = *reinterpret_cast<const float4*>(s_stage + rr * EPI_STAGE_LD + csub);
+          const float4 x4 = xr[cc % XDEPTH][it];
+          *reinterpret_cast<float4*>(xbase + (size_t)rr * p.ldo + col0) =
+              make_float4(x4.x + a4.x, x4.y + a4.y, x4.z + a4.z, x4.w + a4.w);
+        }
       }
-#pragma unroll
-      for (int it = 0; it < 16; ++it) xr[it] = xn[it];
+      if (cc + XDEPTH < NCH) load_resid(cc + XDEPTH, xr[cc % XDEPTH]);  // refill the slot just consumed
       continue;
     }
     if (row_ok) {
