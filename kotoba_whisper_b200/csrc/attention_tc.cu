@@ -30,7 +30,7 @@ namespace tc {
 constexpr int ABQ = 128, ABK = 64, AHD = 64, KV_STAGES = 2;
 constexpr int TILE_BYTES = 128 * 64 * 2;           // Q tile: 16 KB
 constexpr int KV_BYTES = ABK * 64 * 2;             // K, V tiles: 8 KB each
-constexpr int ATT_SM_WARPS = 8;                    // softmax warps: 2 threads per query row (32 keys each)
+constexpr int ATT_SM_WARPS = 4;                    // softmax warps: one thread per query row (all 64 keys of a tile)
 constexpr int ATT_SM_THREADS = ATT_SM_WARPS * 32;
 constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 2);
 constexpr int ATT_TMEM_COLS = 256;                 // S0, S1: 64 columns each; O: 64; P0, P1: 32 each (bf16 pairs)
@@ -74,7 +74,6 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
                      __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
 }
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // softmax threads only
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -169,11 +168,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue: four threads per query row =====================
-    const int quarter = warp & 3, kq = warp >> 2;        // TMEM lane quarter, key half (32 keys)
-    const int r = quarter * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float* s_xchg = reinterpret_cast<float*>(gen_base + OFF_XCHG);  // [2 (tile parity)][2 (key half)][128 rows]
+    // ===================== softmax / correction / epilogue: one thread per query row =====================
+    // No cross-thread exchange: the row maximum, the row sum and the decision to rescale are thread-local, so a tile
+    // costs one tcgen05.ld round trip, the math, one tcgen05.st and two mbarrier arrivals — no smem, no bar.sync.
+    const int r = warp * 32 + lane;                      // query row of the tile = TMEM lane
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
     // Running maximum in the log2 domain (mb = m * log2 e).  It is only moved when a tile's maximum exceeds it by more
     // than RESCALE_T (p <= 2^8 in between: harmless for the fp32 sums and for bf16 P, and the common offset cancels in
@@ -186,38 +185,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int s = j & 1;
       mbar_wait(s_full(s), (j >> 1) & 1);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tmem_base + s * ABK + lane_off + kq * 32, v);
+      uint32_t v[ABK];
+      tmem_ld32(tmem_base + s * ABK + lane_off, v);
+      tmem_ld32(tmem_base + s * ABK + lane_off + 32, v + 32);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
       mbar_arrive(s_empty(s));                            // the scores are in registers: S(j+2) may overwrite the buffer
-      const int kbase = j * ABK + kq * 32;                // first key of this thread's quarter
-      if (kbase + 32 > p.Tk) {
+      const int kbase = j * ABK;                          // first key of the tile
+      if (kbase + ABK > p.Tk) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
+        for (int i = 0; i < ABK; ++i)
           if (kbase + i >= p.Tk) v[i] = 0xff800000u;      // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < ABK; i += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(v[i]));
         mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
       }
-      float* xc = s_xchg + s * 256;
-      xc[kq * 128 + r] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      softmax_bar();
-      const float mt = fmaxf(xc[r], xc[128 + r]) * LOG2E;  // finite: every tile holds >= 1 valid key
+      const float mt = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * LOG2E;  // finite: every tile holds >= 1 valid key
       const bool moved = mt > mb_run + RESCALE_T;           // always on the first tile (mb_run = -inf)
       const float mb = moved ? mt : mb_run;
       const float alpha = moved ? ex2(mb_run - mb) : 1.0f;  // 0 on the first tile
       const float2 nmb = make_float2(-mb, -mb);
       // P(j) -> TMEM buffer j & 1 (its previous reader P(j-2) V(j-2) completed before S(j) did: one in-order MMA pipe)
       float2 rs0 = make_float2(0.0f, 0.0f), rs1 = make_float2(0.0f, 0.0f);
-      uint32_t pk[16];
+      uint32_t pk[ABK / 2];
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
+      for (int i = 0; i < ABK; i += 8) {
         // packed fp32x2 FMA / ADD (sm_100): half the issue slots of the scalar forms
         float2 e[4];
 #pragma unroll
@@ -229,20 +226,22 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         rs0 = __fadd2_rn(rs0, __fadd2_rn(e[0], e[2]));
         rs1 = __fadd2_rn(rs1, __fadd2_rn(e[1], e[3]));
       }
-      // keys [32 kq, 32 kq + 32) of the tile = packed columns [16 kq, 16 kq + 16) of the P buffer, this thread's lane
-      tmem_st16(tmem_base + TM_P + s * (ABK / 2) + lane_off + kq * 16, pk);
+      tmem_st32(tmem_base + TM_P + s * (ABK / 2) + lane_off, pk);  // 64 keys = 32 packed columns of the P buffer
       l_run = l_run * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
       mb_run = mb;
       if (j > 0 && __any_sync(0xffffffffu, moved)) {
         // O is rescaled before P(j) V(j) accumulates on top of it; P(j-1) V(j-1) has to have completed first
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-        uint32_t o[32];
-        tmem_ld32(tO + lane_off + kq * 32, o);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st32(tO + lane_off + kq * 32, o);
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t o[32];
+          tmem_ld32(tO + lane_off + h2 * 32, o);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tO + lane_off + h2 * 32, o);
+        }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // P (and the rescaled O) are in TMEM
       tc_fence_before();
@@ -250,18 +249,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     mbar_wait(o_full, (n_kt - 1) & 1);
     tc_fence_after();
-    // total row sum over the four key quarters (same running max on all of them).  Slot parity n_kt & 1 was last used
-    // by tile n_kt - 2, whose readers all passed the tile n_kt - 1 barrier.
-    float* xc = s_xchg + (n_kt & 1) * 256;
-    xc[kq * 128 + r] = l_run;
-    softmax_bar();
-    const float l_all = xc[r] + xc[128 + r];
     const int t = q0 + r;
-    const float inv = 1.0f / l_all;
-    bf16* orow = p.out + (size_t)b * p.o_sb + (size_t)t * p.o_st + h * AHD + kq * 32;
-    {
+    const float inv = 1.0f / l_run;
+    bf16* orow = p.out + (size_t)b * p.o_sb + (size_t)t * p.o_st + h * AHD;
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
       uint32_t o[32];
-      tmem_ld32(tO + lane_off + kq * 32, o);
+      tmem_ld32(tO + lane_off + h2 * 32, o);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (t < p.Tq) {
 #pragma unroll
@@ -271,7 +265,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           w.y = pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
           w.z = pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
           w.w = pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + i) = w;
+          *reinterpret_cast<uint4*>(orow + h2 * 32 + i) = w;
         }
       }
     }
