@@ -330,9 +330,9 @@ int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d,
   KW_REQUIRE(pos >= 0 && pos < max_t && max_t <= 512, "dec_self_attn: pos=%d max_t=%d", pos, max_t);
   dim3 grid(H, B);
   if (t == KW_BF16)
-    KW_CUDA_OK(launch_pdl(dec_self_attn_kernel<bf16>, grid, dim3(128), 0, st, qkv, (bf16*)kc, (bf16*)vc, (bf16*)out, d, H, max_t, pos));
+    KW_CUDA_OK(launch_pdl(PDL_SELF_ATTN, dec_self_attn_kernel<bf16>, grid, dim3(128), 0, st, qkv, (bf16*)kc, (bf16*)vc, (bf16*)out, d, H, max_t, pos));
   else
-    KW_CUDA_OK(launch_pdl(dec_self_attn_kernel<float>, grid, dim3(128), 0, st, qkv, (float*)kc, (float*)vc, (float*)out, d, H, max_t, pos));
+    KW_CUDA_OK(launch_pdl(PDL_SELF_ATTN, dec_self_attn_kernel<float>, grid, dim3(128), 0, st, qkv, (float*)kc, (float*)vc, (float*)out, d, H, max_t, pos));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;
@@ -456,9 +456,9 @@ int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int
   dim3 grid(H, B);
   const size_t smem = sizeof(float) * S;
   if (t == KW_BF16)
-    KW_CUDA_OK(launch_pdl(dec_cross_attn_kernel<bf16>, grid, dim3(XA_THREADS), smem, st, q, (const bf16*)xkv, (bf16*)out, d, S));
+    KW_CUDA_OK(launch_pdl(PDL_CROSS_ATTN, dec_cross_attn_kernel<bf16>, grid, dim3(XA_THREADS), smem, st, q, (const bf16*)xkv, (bf16*)out, d, S));
   else
-    KW_CUDA_OK(launch_pdl(dec_cross_attn_kernel<float>, grid, dim3(XA_THREADS), smem, st, q, (const float*)xkv, (float*)out, d, S));
+    KW_CUDA_OK(launch_pdl(PDL_CROSS_ATTN, dec_cross_attn_kernel<float>, grid, dim3(XA_THREADS), smem, st, q, (const float*)xkv, (float*)out, d, S));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

@@ -85,19 +85,24 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // kernel in the stream is still draining.  Every kernel launched this way executes griddepcontrol.wait before it touches
 // global memory, so the stream order of memory effects is preserved; the ~2-3 us launch latency of the short decode-step
 // kernels overlaps the predecessor instead of adding to the per-position critical path.
+enum PdlKind { PDL_LN = 1, PDL_SELF_ATTN = 2, PDL_CROSS_ATTN = 4, PDL_EMBED = 8, PDL_SAMPLE = 16 };
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                     Args... args) {
+static inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  static const int enabled = [] {
-    const char* e = getenv("KW_PDL_ALL");
-    return e ? atoi(e) : 0;  // measured on B200: early launch of the small decode kernels costs ~10 ms per 127-step pass
+  static const int mask = [] {
+    const char* e = getenv("KW_PDL_MASK");  // bit set of PdlKind
+    // Measured on B200, greedy pass of 124 positions at B = 64: none 60.5 ms, LN 57.5, LN + self-attention 55.2,
+    // everything but cross-attention 56.3, everything 68.5 (an early-launched cross-attention grid — 1280 CTAs that need
+    // every SM — ends up unevenly placed next to the still-resident GEMM CTAs).
+    return e ? atoi(e) : (PDL_LN | PDL_SELF_ATTN);
   }();
+  const int enabled = mask & kind;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;

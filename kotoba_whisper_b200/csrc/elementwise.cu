@@ -162,8 +162,8 @@ int im2col_conv2(const void* h0, void* A2, int B, int d, int Tin, int Tout, kw_d
 int layernorm(const float* x, const float* w, const float* b, void* out, int rows, int d, kw_dtype t, cudaStream_t st) {
   KW_REQUIRE(d % 4 == 0 && d <= LN_MAX_VEC * 128, "layernorm: d=%d unsupported", d);
   int blocks = ceil_div(rows, 8);
-  if (t == KW_BF16) KW_CUDA_OK(launch_pdl(layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, st, x, w, b, (bf16*)out, rows, d));
-  else KW_CUDA_OK(launch_pdl(layernorm_kernel<float>, dim3(blocks), dim3(256), 0, st, x, w, b, (float*)out, rows, d));
+  if (t == KW_BF16) KW_CUDA_OK(launch_pdl(PDL_LN, layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, st, x, w, b, (bf16*)out, rows, d));
+  else KW_CUDA_OK(launch_pdl(PDL_LN, layernorm_kernel<float>, dim3(blocks), dim3(256), 0, st, x, w, b, (float*)out, rows, d));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;
@@ -172,9 +172,9 @@ int layernorm(const float* x, const float* w, const float* b, void* out, int row
 int embed(const int* tokens, int ld_tokens, int pos, const void* E, const float* P, float* x, int B, int d, int vocab,
           kw_dtype t, cudaStream_t st) {
   if (t == KW_BF16)
-    KW_CUDA_OK(launch_pdl(embed_kernel<bf16>, dim3(B), dim3(128), 0, st, tokens, ld_tokens, pos, (const bf16*)E, P, x, d, vocab));
+    KW_CUDA_OK(launch_pdl(PDL_EMBED, embed_kernel<bf16>, dim3(B), dim3(128), 0, st, tokens, ld_tokens, pos, (const bf16*)E, P, x, d, vocab));
   else
-    KW_CUDA_OK(launch_pdl(embed_kernel<float>, dim3(B), dim3(128), 0, st, tokens, ld_tokens, pos, (const float*)E, P, x, d, vocab));
+    KW_CUDA_OK(launch_pdl(PDL_EMBED, embed_kernel<float>, dim3(B), dim3(128), 0, st, tokens, ld_tokens, pos, (const float*)E, P, x, d, vocab));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

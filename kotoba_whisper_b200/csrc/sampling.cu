@@ -149,7 +149,7 @@ int sample_launch(const float* logits, const unsigned char* flags, const SampleR
                   int B, int pos, int begin_index, int return_ts, int* finished, cudaStream_t st) {
   KW_REQUIRE(pos + 1 < ld_tokens && pos + 1 >= begin_index && begin_index >= 1, "sample: pos=%d begin=%d ld=%d", pos,
              begin_index, ld_tokens);
-  KW_CUDA_OK(launch_pdl(sample_kernel, dim3(B), dim3(SM_THREADS), 0, st, logits, flags, r, tokens, ld_tokens, pos,
+  KW_CUDA_OK(launch_pdl(PDL_SAMPLE, sample_kernel, dim3(B), dim3(SM_THREADS), 0, st, logits, flags, r, tokens, ld_tokens, pos,
                         begin_index, return_ts, finished));
   KW_LAUNCH_OK();
   ++g_launches;
