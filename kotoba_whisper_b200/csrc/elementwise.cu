@@ -62,34 +62,39 @@ __global__ void __launch_bounds__(256) im2col_conv2_kernel(const T* __restrict__
 
 // ---- LayerNorm ---------------------------------------------------------------------------------------------------
 // rows of fp32 x -> (x - mean) * rsqrt(var + 1e-5) * w + b, biased variance, two-pass in registers; one warp per row.
-constexpr int LN_MAX_VEC = 16;  // d <= 16 * 128
+// NV = float4 groups per lane.  d == NV * 128 instantiations (EXACT) carry no bounds checks and exactly NV * 4 data
+// registers, which keeps the kernel at <= 64 registers -> 32 resident warps per SM (the 737 MB encoder pass is a pure
+// HBM stream and needs the loads of many rows in flight); the NV = 16 generic instantiation covers any d <= 2048.
+constexpr int LN_MAX_VEC = 16;
 
-template <typename T>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, T* __restrict__ out, int rows,
-                                                        int d) {
+template <typename T, int NV, bool EXACT>
+__global__ void __launch_bounds__(256, EXACT && NV <= 10 ? 4 : 2)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                 T* __restrict__ out, int rows, int d) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float* xr = x + (size_t)row * d;
-  float4 v[LN_MAX_VEC];
+  float4 v[NV];
   float sum = 0.0f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
-    int c = (i * 32 + lane) * 4;
-    if (c < d) {
-      v[i] = *reinterpret_cast<const float4*>(xr + c);
-      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (EXACT || c < d) v[i] = *reinterpret_cast<const float4*>(xr + c);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (EXACT || c < d) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(sum) / (float)d;
   float sq = 0.0f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
-    int c = (i * 32 + lane) * 4;
-    if (c < d) {
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (EXACT || c < d) {
       float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
       sq += (a * a + b * b) + (cc * cc + dd * dd);
     }
@@ -97,10 +102,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float rstd = rsqrtf(warp_sum(sq) / (float)d + 1e-5f);
   T* orow = out + (size_t)row * d;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_VEC; ++i) {
-    int c = (i * 32 + lane) * 4;
-    if (c < d) {
-      float4 g = *reinterpret_cast<const float4*>(w + c), be = *reinterpret_cast<const float4*>(bias + c);
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (EXACT || c < d) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), be = __ldg(reinterpret_cast<const float4*>(bias + c));
       float4 o;
       o.x = (v[i].x - mean) * rstd * g.x + be.x;
       o.y = (v[i].y - mean) * rstd * g.y + be.y;
@@ -162,8 +167,18 @@ int im2col_conv2(const void* h0, void* A2, int B, int d, int Tin, int Tout, kw_d
 int layernorm(const float* x, const float* w, const float* b, void* out, int rows, int d, kw_dtype t, cudaStream_t st) {
   KW_REQUIRE(d % 4 == 0 && d <= LN_MAX_VEC * 128, "layernorm: d=%d unsupported", d);
   int blocks = ceil_div(rows, 8);
-  if (t == KW_BF16) KW_CUDA_OK(launch_pdl(PDL_LN, layernorm_kernel<bf16>, dim3(blocks), dim3(256), 0, st, x, w, b, (bf16*)out, rows, d));
-  else KW_CUDA_OK(launch_pdl(PDL_LN, layernorm_kernel<float>, dim3(blocks), dim3(256), 0, st, x, w, b, (float*)out, rows, d));
+#define KW_LN_LAUNCH(TT, NV, EX)                                                                                      \
+  KW_CUDA_OK(launch_pdl(PDL_LN, layernorm_kernel<TT, NV, EX>, dim3(blocks), dim3(256), 0, st, x, w, b, (TT*)out, rows, d))
+  if (t == KW_BF16) {
+    if (d == 1280) KW_LN_LAUNCH(bf16, 10, true);       // large / kotoba / teacher
+    else if (d == 384) KW_LN_LAUNCH(bf16, 3, true);    // tiny
+    else KW_LN_LAUNCH(bf16, LN_MAX_VEC, false);
+  } else {
+    if (d == 1280) KW_LN_LAUNCH(float, 10, true);
+    else if (d == 384) KW_LN_LAUNCH(float, 3, true);
+    else KW_LN_LAUNCH(float, LN_MAX_VEC, false);
+  }
+#undef KW_LN_LAUNCH
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

@@ -76,3 +76,10 @@ if "logmel" in what:
             byts = B * (480000 * 4 + nm * 3000 * 4)
             print(f"{'log-mel':28s} n_mels={nm} B={B:5d}  {ms*1e3:9.1f} us  {byts/ms/1e6:8.1f} GB/s  {B/ms*1e3:9.0f} clips/s",
                   flush=True)
+if "ln" in what:
+    rows, d = 96000, 1280
+    x = torch.randn(rows, d, device="cuda"); w = torch.randn(d, device="cuda"); b = torch.randn(d, device="cuda")
+    out = torch.empty(rows, d, device="cuda", dtype=torch.bfloat16)
+    fn = lambda: _lib.check(lib.kw_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), rows, d, BF16, st()))  # noqa: E731
+    ms = timeit(fn, iters=20)
+    print(f"{'encoder LayerNorm':28s} rows={rows} d={d}  {ms*1e3:9.1f} us  {rows*d*6/ms/1e6:8.1f} GB/s", flush=True)
