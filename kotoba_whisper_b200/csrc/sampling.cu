@@ -36,6 +36,31 @@ __device__ __forceinline__ Best warp_best(Best x) {
 }
 
 constexpr int SM_THREADS = 1024;
+constexpr int SM_SPLIT = 4;  // CTAs (one thread-block cluster) per batch row: 64 rows alone would leave 84 SMs idle
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_cluster_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(SM_THREADS)
 sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ flags, SampleRules r,
@@ -44,9 +69,14 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
   __shared__ int s_state[5];  // at_begin, last_ts, pen_ts, has_ts, bound
   __shared__ Best s_text[SM_THREADS / 32], s_ts[SM_THREADS / 32];
   __shared__ float s_sum[SM_THREADS / 32];
+  __shared__ Best s_part_text[SM_SPLIT], s_part_ts[SM_SPLIT];  // per-CTA partials, gathered in the cluster's CTA 0
+  __shared__ float s_part_sum[SM_SPLIT];
   pdl_trigger();
   pdl_wait();
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int crank = (int)cluster_rank();
+  const int b = blockIdx.x / SM_SPLIT, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // this CTA's slice of the vocabulary
+  const int slice = (r.vocab + SM_SPLIT - 1) / SM_SPLIT, v_lo = crank * slice, v_hi = min(r.vocab, v_lo + slice);
   const float* row = logits + (size_t)b * r.vocab;
   int* trow = tokens + (size_t)b * ld_tokens;
 
@@ -93,19 +123,19 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
 
   Best bt = {-INFINITY, r.vocab}, bs = {-INFINITY, r.vocab};
   constexpr int U = 8;  // independent loads in flight per thread (the row is 207 KB: latency-, not bandwidth-bound)
-  for (int v0 = tid; v0 < r.vocab; v0 += U * SM_THREADS) {
+  for (int v0 = v_lo + tid; v0 < v_hi; v0 += U * SM_THREADS) {
     float x[U];
     unsigned char f[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int v = v0 + u * SM_THREADS;
-      x[u] = v < r.vocab ? row[v] : -INFINITY;
-      f[u] = v < r.vocab ? flags[v] : (unsigned char)1;
+      x[u] = v < v_hi ? row[v] : -INFINITY;
+      f[u] = v < v_hi ? flags[v] : (unsigned char)1;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int v = v0 + u * SM_THREADS;
-      if (v >= r.vocab || masked_f(v, f[u])) continue;
+      if (v >= v_hi || masked_f(v, f[u])) continue;
       Best c = {x[u], v};
       if (v < tb) bt = better(bt, c); else bs = better(bs, c);
     }
@@ -114,22 +144,51 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
   bs = warp_best(bs);
   if (lane == 0) { s_text[warp] = bt; s_ts[warp] = bs; }
   __syncthreads();
-  bt = s_text[0];
-  bs = s_ts[0];
-  for (int w = 1; w < SM_THREADS / 32; ++w) { bt = better(bt, s_text[w]); bs = better(bs, s_ts[w]); }
+  // CTA partials -> CTA 0 of the cluster (distributed shared memory), then every CTA reads the row-wide result back
+  if (tid == 0) {
+    bt = s_text[0];
+    bs = s_ts[0];
+    for (int w = 1; w < SM_THREADS / 32; ++w) { bt = better(bt, s_text[w]); bs = better(bs, s_ts[w]); }
+    const uint32_t pt = map_to_rank(smem_addr(&s_part_text[crank]), 0), ps = map_to_rank(smem_addr(&s_part_ts[crank]), 0);
+    st_cluster_u32(pt, __float_as_uint(bt.v));
+    st_cluster_u32(pt + 4, (uint32_t)bt.i);
+    st_cluster_u32(ps, __float_as_uint(bs.v));
+    st_cluster_u32(ps + 4, (uint32_t)bs.i);
+  }
+  cluster_barrier();
+  if (!return_ts && crank != 0) return;  // only the timestamp rule needs a second, row-wide pass
+  {
+    const uint32_t pt = map_to_rank(smem_addr(&s_part_text[0]), 0), ps = map_to_rank(smem_addr(&s_part_ts[0]), 0);
+    bt.v = __uint_as_float(ld_cluster_u32(pt)); bt.i = (int)ld_cluster_u32(pt + 4);
+    bs.v = __uint_as_float(ld_cluster_u32(ps)); bs.i = (int)ld_cluster_u32(ps + 4);
+    for (int c = 1; c < SM_SPLIT; ++c) {  // rank order: ties keep the smaller index, as torch.argmax
+      Best t2, s2;
+      t2.v = __uint_as_float(ld_cluster_u32(pt + 8 * c)); t2.i = (int)ld_cluster_u32(pt + 8 * c + 4);
+      s2.v = __uint_as_float(ld_cluster_u32(ps + 8 * c)); s2.i = (int)ld_cluster_u32(ps + 8 * c + 4);
+      bt = better(bt, t2);
+      bs = better(bs, s2);
+    }
+  }
 
   int choice;
   if (return_ts) {
     // logsumexp over the unmasked timestamp logits vs the best text logit (log_softmax's shift cancels on both sides)
     float part = 0.0f;
     if (bs.v > -INFINITY)
-      for (int v = tb + tid; v < r.vocab; v += SM_THREADS)
+      for (int v = max(tb, v_lo) + tid; v < v_hi; v += SM_THREADS)
         if (!masked(v)) part += expf(row[v] - bs.v);
     part = warp_sum(part);
     if (lane == 0) s_sum[warp] = part;
     __syncthreads();
+    if (tid == 0) {
+      float ctot = 0.0f;
+      for (int w = 0; w < SM_THREADS / 32; ++w) ctot += s_sum[w];
+      st_cluster_u32(map_to_rank(smem_addr(&s_part_sum[crank]), 0), __float_as_uint(ctot));
+    }
+    cluster_barrier();
+    if (crank != 0) return;
     float tot = 0.0f;
-    for (int w = 0; w < SM_THREADS / 32; ++w) tot += s_sum[w];
+    for (int c = 0; c < SM_SPLIT; ++c) tot += s_part_sum[c];
     const float lse = (bs.v > -INFINITY) ? bs.v + logf(tot) : -INFINITY;
     if (lse > bt.v) choice = bs.i;
     else choice = (bt.v >= bs.v) ? bt.i : bs.i;
@@ -149,8 +208,20 @@ int sample_launch(const float* logits, const unsigned char* flags, const SampleR
                   int B, int pos, int begin_index, int return_ts, int* finished, cudaStream_t st) {
   KW_REQUIRE(pos + 1 < ld_tokens && pos + 1 >= begin_index && begin_index >= 1, "sample: pos=%d begin=%d ld=%d", pos,
              begin_index, ld_tokens);
-  KW_CUDA_OK(launch_pdl(PDL_SAMPLE, sample_kernel, dim3(B), dim3(SM_THREADS), 0, st, logits, flags, r, tokens, ld_tokens, pos,
-                        begin_index, return_ts, finished));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(B * SM_SPLIT);
+  cfg.blockDim = dim3(SM_THREADS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = SM_SPLIT;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  KW_CUDA_OK(cudaLaunchKernelEx(&cfg, sample_kernel, logits, flags, r, tokens, ld_tokens, pos, begin_index, return_ts,
+                                finished));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;
