@@ -17,9 +17,10 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--max-length", type=int, default=128)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--enc-layers", type=int, default=0, help="shrink the encoder (same kernel shapes) for --set full captures")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
-cfg = WhisperB200Config(**KOTOBA)
+cfg = WhisperB200Config(**dict(KOTOBA, encoder_layers=a.enc_layers or KOTOBA["encoder_layers"]))
 model = WhisperB200ForConditionalGeneration.from_state_dict(
     random_state_dict(cfg, 0, dev), cfg, dtype=torch.bfloat16 if a.dtype == "bf16" else torch.float32,
     max_batch=a.batch, device=dev)
