@@ -1,22 +1,21 @@
 // tcgen05 flash attention for the Whisper encoder (non-causal, no mask, head dim 64, q pre-scaled; the arithmetic of
 // sdpa_attention_forward as called at modeling_whisper.py:342-352), bf16 operands, fp32 softmax / accumulation.
 //
-// CTA = one 128-query tile of one (batch, head) walking 64-key tiles; two CTAs per SM (256 TMEM columns, 48 KB smem each)
-// so that one CTA's MUFU-bound exp phase overlaps the other's TMEM / barrier latency chain.  The score tile S and
-// the probability tile P are both double buffered in TENSOR MEMORY: the tensor pipe computes S(j+1) while the softmax
-// threads work on S(j), and P(j) V(j) takes its A operand straight from TMEM (no shared-memory round trip for P, which
-// would otherwise cost 64 KB of smem traffic per tile on top of the Q/K/V operand reads) while they start on S(j+1).
-// Per 128-key tile j:
-//   warp 16  TMA:  K and V tiles ([128 keys x 64] bf16, 128 B swizzle, 2 stages each) via 3D tensor maps over the strided
-//                  q/k/v views (coordinates = column, time, batch; out-of-range rows are zero-filled)
-//   warp 17  MMA:  S(j) = Q K_j^T   tcgen05.mma M=128 N=128 K=64 (both K-major)              -> TMEM cols [128 (j&1), +128)
-//                  O += P(j) V_j    tcgen05.mma M=128 N=64  K=128 (P from TMEM cols [320 + 64 (j&1), +64), V MN-major from smem)
-//                                                                                           -> TMEM cols [256, 320)
-//   warps 0-15     four threads per query row (32 keys each; warp w owns TMEM lanes 32*(w%4).. and key quarter w/4):
-//                  one tcgen05.ld of the row's 32 scores (S is released right after it), partial row max exchanged through
-//                  smem, p = exp2(s*log2e - m*log2e), partial row sums, P -> packed bf16 pairs into TMEM (tcgen05.st, 16
-//                  columns per thread), then the rescale of O in TMEM when the running max moved (16 columns per thread).
-// Finally O / l is written as bf16, 32 bytes per thread.
+// CTA = one 128-query tile of one (batch, head) walking 64-key tiles.  Everything but Q / K / V lives in TENSOR MEMORY:
+//   warp 4   TMA:  Q once, then K and V tiles ([64 keys x 64] bf16, 128 B swizzle, 2-slot rings) via 3D tensor maps over the
+//                  strided q/k/v views (coordinates = column, time, batch; out-of-range rows are zero-filled)
+//   warp 5   MMA:  S(j) = Q K_j^T   tcgen05.mma M=128 N=64 K=64 (both K-major)            -> TMEM S  (64 columns)
+//                  O += P(j) V_j    tcgen05.mma M=128 N=64 K=64, A = P straight from TMEM, V MN-major from smem -> TMEM O
+//   warps 0-3      ONE thread per query row: tcgen05.ld of the row's 64 scores, S handed back to the MMA warp at once
+//                  (S(j+1) is computed while this tile's arithmetic runs: the scores in flight live in registers, not
+//                  in a second TMEM buffer), row max / lazy running max, p = exp2(s log2e - m log2e) with packed
+//                  fp32x2 FMA / ADD and MUFU.EX2, row sum, P -> packed bf16 pairs into its own 32 TMEM columns
+//                  (tcgen05.st), O rescaled in TMEM only when the running max moved by more than 2^8.
+// 160 TMEM columns per CTA from TWO allocations (128: S and O; 32: P) and <= 112 registers put THREE CTAs on an SM; their
+// phases interleave on the MUFU, which ends up ~90 % busy (the practical bound at head dim 64: 13.5 exp2 / clk / SM).
+// Measured history of this kernel (B=64, H=20, T=1500, isolated): 2 CTAs/SM with S and P double buffered in 256 columns
+// 638 TFLOP/s; 4 CTAs/SM with P written over S in 128 columns (serial S -> softmax -> PV chain per CTA) 672; this
+// layout 767.  Finally O / l is written as bf16.
 #include <atomic>
 
 #include "tc_common.cuh"
@@ -27,24 +26,12 @@ extern std::atomic<long long> g_launches;
 
 namespace tc {
 
-#ifndef KW_ATT_KV_STAGES
-#define KW_ATT_KV_STAGES 4
-#endif
-// K / V ring depth: a K tile is requested when its slot's previous S MMA retires; with 2 slots that is ~1 tile period
-// (~0.9 us) before the tile is needed — less than a TMA round trip under load — and the softmax threads stalled ~350
-// cycles per tile on the late S (measured with the KW_ATT_TIMING build); 4 slots request it ~3 tiles ahead
-constexpr int ABQ = 128, ABK = 64, AHD = 64, KV_STAGES = KW_ATT_KV_STAGES;
-static_assert((KV_STAGES & (KV_STAGES - 1)) == 0, "KV_STAGES must be a power of two");
+constexpr int ABQ = 128, ABK = 64, AHD = 64;
 constexpr int TILE_BYTES = 128 * 64 * 2;           // Q tile: 16 KB
 constexpr int KV_BYTES = ABK * 64 * 2;             // K, V tiles: 8 KB each
 constexpr int ATT_SM_WARPS = 4;                    // softmax warps: one thread per query row (all 64 keys of a tile)
 constexpr int ATT_SM_THREADS = ATT_SM_WARPS * 32;
 constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 2);
-constexpr int ATT_TMEM_COLS = 256;                 // S0, S1: 64 columns each; O: 64; P0, P1: 32 each (bf16 pairs)
-constexpr int TM_O = 128, TM_P = 192;
-constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = OFF_K + KV_STAGES * KV_BYTES,
-              OFF_BAR = OFF_V + KV_STAGES * KV_BYTES;
-constexpr size_t ATT_SMEM = 1024 + OFF_BAR + 256;
 constexpr uint32_t IDESC_S = make_idesc(128, ABK, 0, 0);
 constexpr uint32_t IDESC_PV = make_idesc(128, 64, 0, 1);  // B = V is MN-major (head dim contiguous)
 
@@ -77,8 +64,9 @@ __device__ __forceinline__ float ex2(float x) {
 // 2^x for x <= 0 on the FMA / ALU pipes instead of the 16-lane MUFU: round-to-nearest split x = n + f, |f| <= 0.5, a
 // degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, 50x below the bf16 rounding of P) and n added into the
 // exponent field.  Inputs below -125 (masked keys: -inf) return ~2^-125 instead of 0; those keys meet all-zero V rows.
-// Measured on B200 (B=64, H=20, T=1500): 0 pairs 609 TFLOP/s, 1 pair of 4: 590, 2 of 4: 564 — the kernel is bound by issue
-// slots and the TMEM / barrier chain, not by MUFU throughput, so the offload is compiled out by default.
+// Measured on B200 (B=64, H=20, T=1500): never a win — 590 / 564 TFLOP/s against 609 at 25 % / 50 % offload on the
+// 2-CTA kernel (latency-chain bound), 406 / 393 against 767 on this kernel (the temporaries spill under the 112-register
+// budget of three CTAs per SM) — so the offload is compiled out by default.
 #ifndef KW_ATT_POLY_PAIRS
 #define KW_ATT_POLY_PAIRS 0  // pairs out of every 4 (8 scores) whose exp2 runs on the FMA pipe
 #endif
@@ -96,26 +84,38 @@ __device__ __forceinline__ float2 ex2_poly2(float2 x) {
                      __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+#ifndef KW_ATT3_KVS
+#define KW_ATT3_KVS 2
+#endif
+namespace a3 {
+constexpr int KVS = KW_ATT3_KVS;
+constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = OFF_K + KVS * KV_BYTES, OFF_BAR = OFF_V + KVS * KV_BYTES;
+// Padded to > 227 KB / 4 so that shared memory, not the register count of some future edit, caps residency at three CTAs
+// per SM: a fourth CTA would take the last 128 TMEM columns and all four would wait forever for their 32-column block.
+constexpr size_t SMEM_USED = 1024 + OFF_BAR + 256;
+constexpr size_t SMEM = SMEM_USED > 58 * 1024 ? SMEM_USED : 58 * 1024;
+static_assert(4 * SMEM > 227 * 1024 && 3 * SMEM <= 227 * 1024, "attn_tc3_kernel must fit exactly three CTAs per SM");
+}  // namespace a3
+
+__global__ void __launch_bounds__(ATT_THREADS, 3)
+attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using namespace a3;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar0 = base + OFF_BAR;
+  const uint32_t bar0 = base + a3::OFF_BAR;
   const uint32_t q_full = bar0;
   auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (1 + KV_STAGES + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * KV_STAGES + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 3 * KV_STAGES + s); };
-  constexpr int BAR_S = 1 + 4 * KV_STAGES;
-  auto s_full = [&](int s) { return bar0 + 8u * (BAR_S + s); };
-  auto s_empty = [&](int s) { return bar0 + 8u * (BAR_S + 2 + s); };
-  auto p_full = [&](int s) { return bar0 + 8u * (BAR_S + 4 + s); };
-  const uint32_t o_full = bar0 + 8u * (BAR_S + 6);
-  const uint32_t tmem_slot = bar0 + 8u * (BAR_S + 7);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + OFF_BAR + 8 * (BAR_S + 7));
-  static_assert(8 * (BAR_S + 8) <= 256, "barrier area");
+  auto k_empty = [&](int s) { return bar0 + 8u * (1 + KVS + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * KVS + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 3 * KVS + s); };
+  constexpr int BS = 1 + 4 * KVS;
+  const uint32_t s_full = bar0 + 8u * BS, s_empty = bar0 + 8u * (BS + 1), p_full = bar0 + 8u * (BS + 2),
+                 o_full = bar0 + 8u * (BS + 3);
+  const uint32_t tmem_slot = bar0 + 8u * (BS + 4);  // two 32-bit slots: the 128-column block, the 32-column block
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + a3::OFF_BAR + 8 * (BS + 4));
+  static_assert(8 * (BS + 5) <= 256, "barrier area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ABQ, h = blockIdx.y, b = blockIdx.z;
@@ -127,82 +127,82 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
     mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
+    for (int s = 0; s < KVS; ++s) {
       mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(s_full(s), 1); mbar_init(s_empty(s), ATT_SM_THREADS); mbar_init(p_full(s), ATT_SM_THREADS);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, ATT_SM_THREADS);
+    mbar_init(p_full, ATT_SM_THREADS);
     mbar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == W_MMA) tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+  if (warp == W_MMA) {  // both allocations, then the permit is given up (three resident CTAs: 480 of 512 columns)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(128) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot + 4), "r"(32) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tO = tmem_base + TM_O;
+  const uint32_t tmem_a = tmem_slot_ptr[0], tmem_b = tmem_slot_ptr[1];
+  const uint32_t tS = tmem_a, tO = tmem_a + 64, tP = tmem_b;
 
   if (warp == W_TMA) {
-    // ===================== TMA producer =====================
     if (lane == 0) {
       mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(base + OFF_Q, &tmQ, q_full, h * AHD, q0, b);
+      tma_load_3d(base + a3::OFF_Q, &tmQ, q_full, h * AHD, q0, b);
       for (int j = 0; j < n_kt; ++j) {
-        const int s = j % KV_STAGES;
-        const uint32_t ph = ((j / KV_STAGES) & 1) ^ 1;  // passes immediately the first time round
+        const int s = j % KVS;
+        const uint32_t ph = ((j / KVS) & 1) ^ 1;  // passes immediately the first time round
         mbar_wait(k_empty(s), ph);
         mbar_expect_tx(k_full(s), KV_BYTES);
-        tma_load_3d(base + OFF_K + s * KV_BYTES, &tmK, k_full(s), h * AHD, j * ABK, b);
+        tma_load_3d(base + a3::OFF_K + s * KV_BYTES, &tmK, k_full(s), h * AHD, j * ABK, b);
         mbar_wait(v_empty(s), ph);
         mbar_expect_tx(v_full(s), KV_BYTES);
-        tma_load_3d(base + OFF_V + s * KV_BYTES, &tmV, v_full(s), h * AHD, j * ABK, b);
+        tma_load_3d(base + a3::OFF_V + s * KV_BYTES, &tmV, v_full(s), h * AHD, j * ABK, b);
       }
     }
   } else if (warp == W_MMA) {
-    // ===================== MMA issuer =====================
     if (lane == 0) {
       mbar_wait(q_full, 0);
-      const uint64_t dq = make_desc(base + OFF_Q);
-      auto issue_S = [&](int j) {  // S(j) = Q K_j^T into S buffer j & 1
-        const int s = j & 1, ks = j % KV_STAGES;
-        mbar_wait(k_full(ks), (j / KV_STAGES) & 1);
-        mbar_wait(s_empty(s), ((j >> 1) & 1) ^ 1);  // softmax has pulled S(j-2) out of this buffer
+      const uint64_t dq = make_desc(base + a3::OFF_Q);
+      auto issue_S = [&](int j) {
+        const int ks = j % KVS;
+        mbar_wait(k_full(ks), (j / KVS) & 1);
         tc_fence_after();
-        const uint64_t dk = make_desc(base + OFF_K + ks * KV_BYTES);
+        const uint64_t dk = make_desc(base + a3::OFF_K + ks * KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < AHD / 16; ++k) umma_f16(tmem_base + s * ABK, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
-        umma_commit(s_full(s));
+        for (int k = 0; k < AHD / 16; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
+        umma_commit(s_full);
         umma_commit(k_empty(ks));
       };
       issue_S(0);
-      if (n_kt > 1) issue_S(1);
       for (int j = 0; j < n_kt; ++j) {
-        const int s = j & 1, vs = j % KV_STAGES;
-        mbar_wait(p_full(s), (j >> 1) & 1);  // P(j) written, O rescaled
-        mbar_wait(v_full(vs), (j / KV_STAGES) & 1);
+        const int vs = j % KVS;
+        if (j + 1 < n_kt) {
+          mbar_wait(s_empty, j & 1);  // every row's S(j) is in registers
+          issue_S(j + 1);
+        }
+        mbar_wait(p_full, j & 1);  // P(j) written, O rescaled
+        mbar_wait(v_full(vs), (j / KVS) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < ABK / 16; ++k) {
-          const uint64_t dv = make_desc_sw128(base + OFF_V + vs * KV_BYTES + k * p.v_kstep, p.v_lbo, p.v_sbo);
-          umma_f16_ts(tO, tmem_base + TM_P + s * (ABK / 2) + k * 8, dv, IDESC_PV, (j | k) != 0);  // 16 keys = 8 packed columns
+          const uint64_t dv = make_desc_sw128(base + a3::OFF_V + vs * KV_BYTES + k * p.v_kstep, p.v_lbo, p.v_sbo);
+          umma_f16_ts(tO, tP + k * 8, dv, IDESC_PV, (j | k) != 0);  // 16 keys = 8 packed columns
         }
         umma_commit(o_full);
         umma_commit(v_empty(vs));
-        if (j + 2 < n_kt) issue_S(j + 2);
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue: one thread per query row =====================
-    // No cross-thread exchange: the row maximum, the row sum and the decision to rescale are thread-local, so a tile
-    // costs one tcgen05.ld round trip, the math, one tcgen05.st and two mbarrier arrivals — no smem, no bar.sync.
     const int r = warp * 32 + lane;                      // query row of the tile = TMEM lane
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
     // Running maximum in the log2 domain (mb = m * log2 e).  It is only moved when a tile's maximum exceeds it by more
     // than RESCALE_T (p <= 2^8 in between: harmless for the fp32 sums and for bf16 P, and the common offset cancels in
-    // O / l exactly as with the tight maximum), so the TMEM round trip that rescales O — and the wait for the previous
-    // P V product in front of it — happens a few times per row block instead of on nearly every tile.
+    // O / l exactly as with the tight maximum), so the TMEM round trip that rescales O happens a few times per row block
+    // instead of on nearly every tile.
     constexpr float RESCALE_T = 8.0f;
     float mb_run = -INFINITY, l_run = 0.0f;
     const float2 L2 = make_float2(LOG2E, LOG2E);
@@ -210,18 +210,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbg_t = clock64();
 #endif
     for (int j = 0; j < n_kt; ++j) {
-      const int s = j & 1;
-      mbar_wait(s_full(s), (j >> 1) & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
       ATT_T(0);
       uint32_t v[ABK];
-      tmem_ld32(tmem_base + s * ABK + lane_off, v);
-      tmem_ld32(tmem_base + s * ABK + lane_off + 32, v + 32);
+      tmem_ld32(tS + lane_off, v);
+      tmem_ld32(tS + lane_off + 32, v + 32);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       tc_fence_before();
-      mbar_arrive(s_empty(s));                            // the scores are in registers: S(j+2) may overwrite the buffer
+      mbar_arrive(s_empty);                               // S(j+1) may overwrite the score columns now
       ATT_T(1);
-      const int kbase = j * ABK;                          // first key of the tile
+      const int kbase = j * ABK;
       if (kbase + ABK > p.Tk) {
 #pragma unroll
         for (int i = 0; i < ABK; ++i)
@@ -241,12 +240,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float alpha = moved ? ex2(mb_run - mb) : 1.0f;  // 0 on the first tile
       const float2 nmb = make_float2(-mb, -mb);
       ATT_T(2);
-      // P(j) -> TMEM buffer j & 1 (its previous reader P(j-2) V(j-2) completed before S(j) did: one in-order MMA pipe)
       float2 rs0 = make_float2(0.0f, 0.0f), rs1 = make_float2(0.0f, 0.0f);
       uint32_t pk[ABK / 2];
 #pragma unroll
       for (int i = 0; i < ABK; i += 8) {
-        // packed fp32x2 FMA / ADD (sm_100): half the issue slots of the scalar forms
         float2 e[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -257,255 +254,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         rs0 = __fadd2_rn(rs0, __fadd2_rn(e[0], e[2]));
         rs1 = __fadd2_rn(rs1, __fadd2_rn(e[1], e[3]));
       }
-      tmem_st32(tmem_base + TM_P + s * (ABK / 2) + lane_off, pk);  // 64 keys = 32 packed columns of the P buffer
       l_run = l_run * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
       mb_run = mb;
       ATT_T(3);
-      if (j > 0 && __any_sync(0xffffffffu, moved)) {
-        // O is rescaled before P(j) V(j) accumulates on top of it; P(j-1) V(j-1) has to have completed first
+      if (j > 0) {  // P(j-1) V(j-1) complete: the P columns are free again and O is stable
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t o[32];
-          tmem_ld32(tO + lane_off + h2 * 32, o);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tO + lane_off + h2 * 32, o);
-        }
       }
       ATT_T(4);
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // P (and the rescaled O) are in TMEM
-      tc_fence_before();
-      mbar_arrive(p_full(s));
-      ATT_T(5);
-    }
-    mbar_wait(o_full, (n_kt - 1) & 1);
-    tc_fence_after();
-    ATT_T(6);
-#ifdef KW_ATT_TIMING
-    if (threadIdx.x == 0)
-      for (int i = 0; i < 7; ++i) atomicAdd(&g_att_dbg[i], (unsigned long long)dbg_acc[i]);
-    if (threadIdx.x == 0) atomicAdd(&g_att_dbg[7], 1ull);
-#endif
-    const int t = q0 + r;
-    const float inv = 1.0f / l_run;
-    bf16* orow = p.out + (size_t)b * p.o_sb + (size_t)t * p.o_st + h * AHD;
-#pragma unroll
-    for (int h2 = 0; h2 < 2; ++h2) {
-      uint32_t o[32];
-      tmem_ld32(tO + lane_off + h2 * 32, o);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (t < p.Tq) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
-          w.y = pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-          w.z = pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-          w.w = pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + h2 * 32 + i) = w;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == W_MMA) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Four-CTAs-per-SM variant.  The kernel above keeps S double buffered (256 TMEM columns per CTA -> two CTAs per SM, eight
-// softmax warps per SM), and its per-phase cycle counters (KW_ATT_TIMING) show the 64 MUFU.EX2 of a tile taking ~800
-// cycles instead of 512 while the MUFU pipe idles through the tcgen05.ld / max / tcgen05.st / mbarrier phases of both
-// CTAs.  Here a CTA owns only 128 TMEM columns — S (64) with P written over its upper half once the scores are in
-// registers, and O (64) — so FOUR CTAs fit on an SM (16 softmax warps, <= 85 registers per thread).  Inside a CTA the
-// chain S(j) -> softmax(j) -> P V(j) -> S(j+1) is serial; the other three CTAs fill the tensor and MUFU pipes meanwhile.
-// Scores are read in two 32-column chunks: chunk 0 only for its maximum and again for its exponentials (TMEM reads are
-// cheap), chunk 1 stays in registers in between, which keeps the thread under the register budget.
-namespace a4 {
-constexpr int KVS = 2;
-constexpr int OFF_Q = 0, OFF_K = TILE_BYTES, OFF_V = OFF_K + KVS * KV_BYTES, OFF_BAR = OFF_V + KVS * KV_BYTES;
-constexpr size_t SMEM = 1024 + OFF_BAR + 128;
-constexpr int TMEM_COLS = 128, TM_S = 0, TM_P = 32, TM_O = 64;  // P (32 packed columns) overwrites S columns 32..63
-}  // namespace a4
-
-#ifndef KW_ATT4_MIN_CTAS
-#define KW_ATT4_MIN_CTAS 4
-#endif
-__global__ void __launch_bounds__(ATT_THREADS, KW_ATT4_MIN_CTAS)
-attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using namespace a4;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar0 = base + a4::OFF_BAR;
-  const uint32_t q_full = bar0;
-  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (3 + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (5 + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (7 + s); };
-  const uint32_t s_full = bar0 + 8u * 9, p_full = bar0 + 8u * 10, o_full = bar0 + 8u * 11;
-  const uint32_t tmem_slot = bar0 + 8u * 12;
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + a4::OFF_BAR + 8 * 12);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ABQ, h = blockIdx.y, b = blockIdx.z;
-  const int n_kt = (p.Tk + ABK - 1) / ABK;
-  constexpr int W_TMA = ATT_SM_WARPS, W_MMA = W_TMA + 1;
-
-  if (warp == W_TMA && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KVS; ++s) {
-      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, ATT_SM_THREADS);
-    mbar_init(o_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == W_MMA) tmem_alloc(tmem_slot, a4::TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t tS = tmem_base + TM_S, tP = tmem_base + a4::TM_P, tO = tmem_base + a4::TM_O;
-
-  if (warp == W_TMA) {
-    if (lane == 0) {
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(base + a4::OFF_Q, &tmQ, q_full, h * AHD, q0, b);
-      for (int j = 0; j < n_kt; ++j) {
-        const int s = j % KVS;
-        const uint32_t ph = ((j / KVS) & 1) ^ 1;  // passes immediately the first time round
-        mbar_wait(k_empty(s), ph);
-        mbar_expect_tx(k_full(s), KV_BYTES);
-        tma_load_3d(base + a4::OFF_K + s * KV_BYTES, &tmK, k_full(s), h * AHD, j * ABK, b);
-        mbar_wait(v_empty(s), ph);
-        mbar_expect_tx(v_full(s), KV_BYTES);
-        tma_load_3d(base + a4::OFF_V + s * KV_BYTES, &tmV, v_full(s), h * AHD, j * ABK, b);
-      }
-    }
-  } else if (warp == W_MMA) {
-    if (lane == 0) {
-      mbar_wait(q_full, 0);
-      const uint64_t dq = make_desc(base + a4::OFF_Q);
-      auto issue_S = [&](int j) {  // S(j) = Q K_j^T; the previous reader of these columns, P(j-1) V(j-1), was issued earlier
-        const int ks = j % KVS;    // on the same in-order MMA pipe
-        mbar_wait(k_full(ks), (j / KVS) & 1);
-        tc_fence_after();
-        const uint64_t dk = make_desc(base + a4::OFF_K + ks * KV_BYTES);
-#pragma unroll
-        for (int k = 0; k < AHD / 16; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
-        umma_commit(s_full);
-        umma_commit(k_empty(ks));
-      };
-      issue_S(0);
-      for (int j = 0; j < n_kt; ++j) {
-        const int vs = j % KVS;
-        mbar_wait(p_full, j & 1);  // P(j) written, O rescaled
-        mbar_wait(v_full(vs), (j / KVS) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < ABK / 16; ++k) {
-          const uint64_t dv = make_desc_sw128(base + a4::OFF_V + vs * KV_BYTES + k * p.v_kstep, p.v_lbo, p.v_sbo);
-          umma_f16_ts(tO, tP + k * 8, dv, IDESC_PV, (j | k) != 0);  // 16 keys = 8 packed columns
-        }
-        umma_commit(v_empty(vs));
-        if (j + 1 < n_kt) issue_S(j + 1);
-        else umma_commit(o_full);
-      }
-    }
-  } else {
-    const int r = warp * 32 + lane;                      // query row of the tile = TMEM lane
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    const float LOG2E = 1.4426950408889634f;
-    constexpr float RESCALE_T = 8.0f;                    // lazy running maximum: see attn_tc_kernel
-    float mb_run = -INFINITY, l_run = 0.0f;
-    const float2 L2 = make_float2(LOG2E, LOG2E);
-    auto row_max = [&](const uint32_t* v) {
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(v[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(v[i + 3]));
-      }
-      return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-    };
-#ifdef KW_ATT_TIMING
-    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbg_t = clock64();
-#endif
-    for (int j = 0; j < n_kt; ++j) {
-      mbar_wait(s_full, j & 1);  // S(j) complete — and with it every earlier MMA, P(j-1) V(j-1) included
-      tc_fence_after();
-      ATT_T(0);
-      const int kbase = j * ABK;
-      const bool ragged = kbase + ABK > p.Tk;
-      // chunk 0 (keys 0..31): maximum only — its registers are free again before chunk 1 arrives (85-register budget)
-      uint32_t v0[32], v1[32];
-      tmem_ld32(tS + lane_off, v0);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (ragged) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + i >= p.Tk) v0[i] = 0xff800000u;       // -inf
-      }
-      const float m0 = row_max(v0);
-      ATT_T(1);
-      tmem_ld32(tS + lane_off + 32, v1);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (ragged) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + 32 + i >= p.Tk) v1[i] = 0xff800000u;
-      }
-      const float mt = fmaxf(m0, row_max(v1)) * LOG2E;  // finite: every tile holds >= 1 valid key
-      const bool moved = mt > mb_run + RESCALE_T;                // always on the first tile (mb_run = -inf)
-      const float mb = moved ? mt : mb_run;
-      const float alpha = moved ? ex2(mb_run - mb) : 1.0f;       // 0 on the first tile
-      const float2 nmb = make_float2(-mb, -mb);
-      ATT_T(2);
-      float2 rs0 = make_float2(0.0f, 0.0f), rs1 = make_float2(0.0f, 0.0f);
-      auto exp_chunk = [&](const uint32_t* v, uint32_t* pk) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float2 e[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i + 2 * q]), __uint_as_float(v[i + 2 * q + 1])), L2, nmb);
-            e[q] = make_float2(ex2(x.x), ex2(x.y));  // exp2(-inf) = 0: masked keys
-            pk[(i >> 1) + q] = pack_bf16(e[q].x, e[q].y);
-          }
-          rs0 = __fadd2_rn(rs0, __fadd2_rn(e[0], e[2]));
-          rs1 = __fadd2_rn(rs1, __fadd2_rn(e[1], e[3]));
-        }
-      };
-      // keys 32..63 first: their packed columns (TM_P + 16..31 = S columns 48..63) lie inside the chunk just consumed
-      uint32_t pk[16];
-      exp_chunk(v1, pk);
-      tmem_st16(tP + lane_off + 16, pk);
-      ATT_T(3);
-      // keys 0..31: S columns 0..31 are untouched by the store above; read them again, then fill S columns 32..47
-      tmem_ld32(tS + lane_off, v0);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (ragged) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + i >= p.Tk) v0[i] = 0xff800000u;
-      }
-      exp_chunk(v0, pk);
-      tmem_st16(tP + lane_off, pk);
-      l_run = l_run * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
-      mb_run = mb;
-      ATT_T(4);
-      if (j > 0 && __any_sync(0xffffffffu, moved)) {  // P(j-1) V(j-1) is complete (s_full above): O may be rescaled
+      tmem_st32(tP + lane_off, pk);
+      if (j > 0 && __any_sync(0xffffffffu, moved)) {
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           uint32_t o[32];
@@ -521,13 +279,14 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive(p_full);
       ATT_T(5);
     }
-    mbar_wait(o_full, 0);
+    mbar_wait(o_full, (n_kt - 1) & 1);
     tc_fence_after();
     ATT_T(6);
 #ifdef KW_ATT_TIMING
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
       for (int i = 0; i < 7; ++i) atomicAdd(&g_att_dbg[i], (unsigned long long)dbg_acc[i]);
-    if (threadIdx.x == 0) atomicAdd(&g_att_dbg[7], 1ull);
+      atomicAdd(&g_att_dbg[7], 1ull);
+    }
 #endif
     const int t = q0 + r;
     const float inv = 1.0f / l_run;
@@ -552,7 +311,10 @@ attn_tc4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == W_MMA) tmem_dealloc(tmem_base, a4::TMEM_COLS);
+  if (warp == W_MMA) {
+    tmem_dealloc(tmem_a, 128);
+    tmem_dealloc(tmem_b, 32);
+  }
 }
 
 static int make_map3(CUtensorMap* map, const void* ptr, int B, int T, int H, long long sb, long long st, int box_rows) {
@@ -572,8 +334,8 @@ void attention_tc_debug(int lbo, int sbo, int kstep) {
     unsigned long long h[8], z[8] = {0};
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(h, tc::g_att_dbg, sizeof(h));
-    const char* nm[7] = {"0 wait s_full", "1 ld (+arrive) [4: ld c0 + max]", "2 max + alpha [4: ld c1 + max]", "3 exp all + st [4: exp c1 + st]",
-                         "4 rescale [4: ld c0 + exp c0 + st]", "5 wait::st + arrive [4: + rescale]", "6 final o_full wait"};
+    const char* nm[7] = {"0 wait S(j)", "1 tcgen05.ld scores + release S", "2 mask + max + alpha", "3 ffma / ex2 / pack / sum",
+                         "4 wait PV(j-1)", "5 st P (+ rare O rescale) + arrive", "6 final wait for O"};
     const double ctas = (double)h[7];
     for (int i = 0; i < 7; ++i) fprintf(stderr, "  att phase %-32s %10.1f cycles per CTA\n", nm[i], h[i] / ctas);
     cudaMemcpyToSymbol(tc::g_att_dbg, z, sizeof(z));
@@ -597,19 +359,15 @@ int attention_tc(const void* q, const void* k, const void* v, void* out, int B, 
   if ((rc = make_map3(&tmK, k, B, Tk, H, kv_sb, kv_st, ABK))) return rc;
   if ((rc = make_map3(&tmV, v, B, Tk, H, kv_sb, kv_st, ABK))) return rc;
   static bool attr = false;
-  static int variant = 4;  // CTAs per SM: 4 = attn_tc4_kernel, 2 = attn_tc_kernel (KW_ATT_VARIANT for A/B runs)
   if (!attr) {
-    KW_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM));
-    KW_CUDA_OK(cudaFuncSetAttribute(attn_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a4::SMEM));
-    if (const char* e = getenv("KW_ATT_VARIANT")) variant = atoi(e);
+    KW_CUDA_OK(cudaFuncSetAttribute(attn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a3::SMEM));
     attr = true;
   }
   AttnParams p;
   p.out = (bf16*)out; p.o_sb = o_sb; p.o_st = o_st; p.Tq = Tq; p.Tk = Tk;
   p.v_lbo = g_v_lbo; p.v_sbo = g_v_sbo; p.v_kstep = g_v_kstep;
   dim3 grid(ceil_div(Tq, ABQ), H, B);
-  if (variant == 4) attn_tc4_kernel<<<grid, ATT_THREADS, a4::SMEM, st>>>(tmQ, tmK, tmV, p);
-  else attn_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  attn_tc3_kernel<<<grid, ATT_THREADS, a3::SMEM, st>>>(tmQ, tmK, tmV, p);
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;
