@@ -64,25 +64,23 @@ __device__ __forceinline__ float ex2(float x) {
 // 2^x for x <= 0 on the FMA / ALU pipes instead of the 16-lane MUFU: round-to-nearest split x = n + f, |f| <= 0.5, a
 // degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, 50x below the bf16 rounding of P) and n added into the
 // exponent field.  Inputs below -125 (masked keys: -inf) return ~2^-125 instead of 0; those keys meet all-zero V rows.
-// Measured on B200 (B=64, H=20, T=1500): never a win — 590 / 564 TFLOP/s against 609 at 25 % / 50 % offload on the
-// 2-CTA kernel (latency-chain bound), 406 / 393 against 767 on this kernel (the temporaries spill under the 112-register
-// budget of three CTAs per SM) — so the offload is compiled out by default.
+// Measured on B200 (B=64, H=20, T=1500): never a win — 590 / 564 TFLOP/s against 609 at 25 % / 50 % offload on the earlier
+// 2-CTA kernel (latency-chain bound), 204-406 against 767 on this kernel: three CTAs of 6 warps put 5 warps on some
+// schedulers, which caps the kernel at 96 registers, exactly what the plain loop needs — the polynomial's temporaries
+// spill.  Compiled out by default.
 #ifndef KW_ATT_POLY_PAIRS
 #define KW_ATT_POLY_PAIRS 0  // pairs out of every 4 (8 scores) whose exp2 runs on the FMA pipe
 #endif
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  x.x = fmaxf(x.x, -125.0f);
-  x.y = fmaxf(x.y, -125.0f);
-  const float2 t = __fadd2_rn(x, make_float2(12582912.0f, 12582912.0f));  // 1.5 * 2^23: mantissa low bits = round(x)
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = __ffma2_rn(n, make_float2(-1.0f, -1.0f), x);
-  float2 q = __ffma2_rn(make_float2(0.05517125502228737f, 0.05517125502228737f), f,
-                        make_float2(0.2426103800535202f, 0.2426103800535202f));
-  q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  q = __ffma2_rn(q, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
-  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
-                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+__device__ __forceinline__ float ex2_poly(float x) {  // scalar form: every constant is an instruction immediate
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: mantissa low bits = round(x)
+  const float f = x - (t - 12582912.0f);
+  float q = fmaf(0.05517125502228737f, f, 0.2426103800535202f);
+  q = fmaf(q, f, 0.6932609677314758f);
+  q = fmaf(q, f, 0.9999281167984009f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
 }
+__device__ __forceinline__ float2 ex2_poly2(float2 x) { return make_float2(ex2_poly(x.x), ex2_poly(x.y)); }
 
 #ifndef KW_ATT3_KVS
 #define KW_ATT3_KVS 2
