@@ -2,16 +2,17 @@
 // sdpa_attention_forward as called at modeling_whisper.py:342-352), bf16 operands, fp32 softmax / accumulation.
 //
 // CTA = one 128-query tile of one (batch, head) walking 64-key tiles.  Everything but Q / K / V lives in TENSOR MEMORY:
-//   warp 4   TMA:  Q once, then K and V tiles ([64 keys x 64] bf16, 128 B swizzle, 2-slot rings) via 3D tensor maps over the
+//   warp 4, lane 0 issues both the loads and the MMAs:
+//            TMA:  Q once, then K and V tiles ([64 keys x 64] bf16, 128 B swizzle, 3-slot rings) via 3D tensor maps over the
 //                  strided q/k/v views (coordinates = column, time, batch; out-of-range rows are zero-filled)
-//   warp 5   MMA:  S(j) = Q K_j^T   tcgen05.mma M=128 N=64 K=64 (both K-major)            -> TMEM S  (64 columns)
+//            MMA:  S(j) = Q K_j^T   tcgen05.mma M=128 N=64 K=64 (both K-major)            -> TMEM S  (64 columns)
 //                  O += P(j) V_j    tcgen05.mma M=128 N=64 K=64, A = P straight from TMEM, V MN-major from smem -> TMEM O
 //   warps 0-3      ONE thread per query row: tcgen05.ld of the row's 64 scores, S handed back to the MMA warp at once
 //                  (S(j+1) is computed while this tile's arithmetic runs: the scores in flight live in registers, not
 //                  in a second TMEM buffer), row max / lazy running max, p = exp2(s log2e - m log2e) with packed
 //                  fp32x2 FMA / ADD and MUFU.EX2, row sum, P -> packed bf16 pairs into its own 32 TMEM columns
 //                  (tcgen05.st), O rescaled in TMEM only when the running max moved by more than 2^8.
-// 160 TMEM columns per CTA from TWO allocations (128: S and O; 32: P) and <= 112 registers put THREE CTAs on an SM; their
+// 160 TMEM columns per CTA from TWO allocations (128: S and O; 32: P) and <= 128 registers put THREE CTAs on an SM; their
 // phases interleave on the MUFU, which ends up ~90 % busy (the practical bound at head dim 64: 13.5 exp2 / clk / SM).
 // Measured history of this kernel (B=64, H=20, T=1500, isolated): 2 CTAs/SM with S and P double buffered in 256 columns
 // 638 TFLOP/s; 4 CTAs/SM with P written over S in 128 columns (serial S -> softmax -> PV chain per CTA) 672; this
@@ -31,7 +32,7 @@ constexpr int TILE_BYTES = 128 * 64 * 2;           // Q tile: 16 KB
 constexpr int KV_BYTES = ABK * 64 * 2;             // K, V tiles: 8 KB each
 constexpr int ATT_SM_WARPS = 4;                    // softmax warps: one thread per query row (all 64 keys of a tile)
 constexpr int ATT_SM_THREADS = ATT_SM_WARPS * 32;
-constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 2);
+constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 1);   // + one warp whose lane 0 issues both the TMA loads and the MMAs
 constexpr uint32_t IDESC_S = make_idesc(128, ABK, 0, 0);
 constexpr uint32_t IDESC_PV = make_idesc(128, 64, 0, 1);  // B = V is MN-major (head dim contiguous)
 
@@ -65,9 +66,8 @@ __device__ __forceinline__ float ex2(float x) {
 // degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, 50x below the bf16 rounding of P) and n added into the
 // exponent field.  Inputs below -125 (masked keys: -inf) return ~2^-125 instead of 0; those keys meet all-zero V rows.
 // Measured on B200 (B=64, H=20, T=1500): never a win — 590 / 564 TFLOP/s against 609 at 25 % / 50 % offload on the earlier
-// 2-CTA kernel (latency-chain bound), 204-406 against 767 on this kernel: three CTAs of 6 warps put 5 warps on some
-// schedulers, which caps the kernel at 96 registers, exactly what the plain loop needs — the polynomial's temporaries
-// spill.  Compiled out by default.
+// 2-CTA kernel (latency-chain bound), 743 / 652 against 767 on this kernel (111 / 128 registers, no spills): a warp's own
+// instruction stream, not the shared MUFU, sets the length of its exp phase.  Compiled out by default.
 #ifndef KW_ATT_POLY_PAIRS
 #define KW_ATT_POLY_PAIRS 0  // pairs out of every 4 (8 scores) whose exp2 runs on the FMA pipe
 #endif
@@ -83,7 +83,7 @@ __device__ __forceinline__ float ex2_poly(float x) {  // scalar form: every cons
 __device__ __forceinline__ float2 ex2_poly2(float2 x) { return make_float2(ex2_poly(x.x), ex2_poly(x.y)); }
 
 #ifndef KW_ATT3_KVS
-#define KW_ATT3_KVS 2
+#define KW_ATT3_KVS 3
 #endif
 namespace a3 {
 constexpr int KVS = KW_ATT3_KVS;
@@ -105,28 +105,28 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t bar0 = base + a3::OFF_BAR;
   const uint32_t q_full = bar0;
   auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (1 + KVS + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * KVS + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 3 * KVS + s); };
-  constexpr int BS = 1 + 4 * KVS;
+  auto v_full = [&](int s) { return bar0 + 8u * (1 + KVS + s); };
+  constexpr int BS = 1 + 2 * KVS;
   const uint32_t s_full = bar0 + 8u * BS, s_empty = bar0 + 8u * (BS + 1), p_full = bar0 + 8u * (BS + 2),
                  o_full = bar0 + 8u * (BS + 3);
   const uint32_t tmem_slot = bar0 + 8u * (BS + 4);  // two 32-bit slots: the 128-column block, the 32-column block
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + a3::OFF_BAR + 8 * (BS + 4));
   static_assert(8 * (BS + 5) <= 256, "barrier area");
+  static_assert(KVS == 3, "the slot-reuse argument of the issuing thread below is written for a 3-slot ring");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * ABQ, h = blockIdx.y, b = blockIdx.z;
   const int n_kt = (p.Tk + ABK - 1) / ABK;
-  constexpr int W_TMA = ATT_SM_WARPS, W_MMA = W_TMA + 1;
+  constexpr int W_MMA = ATT_SM_WARPS;
 
-  if (warp == W_TMA && lane == 0) {
+  if (warp == W_MMA && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
     mbar_init(q_full, 1);
     for (int s = 0; s < KVS; ++s) {
-      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(k_full(s), 1);
+      mbar_init(v_full(s), 1);
     }
     mbar_init(s_full, 1);
     mbar_init(s_empty, ATT_SM_THREADS);
@@ -145,23 +145,29 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_a = tmem_slot_ptr[0], tmem_b = tmem_slot_ptr[1];
   const uint32_t tS = tmem_a, tO = tmem_a + 64, tP = tmem_b;
 
-  if (warp == W_TMA) {
+  if (warp == W_MMA) {
+    // ===================== TMA + MMA issue: one thread =====================
+    // No producer warp and no "slot empty" barriers: by the time this thread has seen p_full(j), S(j) has retired (the
+    // softmax threads read it), so K slot j % 3 is free for K(j+3); and every softmax thread waited for P(j-1) V(j-1)
+    // before it arrived on p_full(j), so V slot (j-1) % 3 is free for V(j+2).  Five warps per CTA also make 15 warps
+    // per SM, which divide over the four schedulers without the fifth warp that capped the kernel at 96 registers.
     if (lane == 0) {
-      mbar_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(base + a3::OFF_Q, &tmQ, q_full, h * AHD, q0, b);
-      for (int j = 0; j < n_kt; ++j) {
+      auto load_k = [&](int j) {
         const int s = j % KVS;
-        const uint32_t ph = ((j / KVS) & 1) ^ 1;  // passes immediately the first time round
-        mbar_wait(k_empty(s), ph);
         mbar_expect_tx(k_full(s), KV_BYTES);
         tma_load_3d(base + a3::OFF_K + s * KV_BYTES, &tmK, k_full(s), h * AHD, j * ABK, b);
-        mbar_wait(v_empty(s), ph);
+      };
+      auto load_v = [&](int j) {
+        const int s = j % KVS;
         mbar_expect_tx(v_full(s), KV_BYTES);
         tma_load_3d(base + a3::OFF_V + s * KV_BYTES, &tmV, v_full(s), h * AHD, j * ABK, b);
+      };
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(base + a3::OFF_Q, &tmQ, q_full, h * AHD, q0, b);
+      for (int j = 0; j < KVS && j < n_kt; ++j) {
+        load_k(j);
+        load_v(j);
       }
-    }
-  } else if (warp == W_MMA) {
-    if (lane == 0) {
       mbar_wait(q_full, 0);
       const uint64_t dq = make_desc(base + a3::OFF_Q);
       auto issue_S = [&](int j) {
@@ -172,7 +178,6 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < AHD / 16; ++k) umma_f16(tS, dq + 2 * k, dk + 2 * k, IDESC_S, k != 0);
         umma_commit(s_full);
-        umma_commit(k_empty(ks));
       };
       issue_S(0);
       for (int j = 0; j < n_kt; ++j) {
@@ -190,7 +195,8 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_f16_ts(tO, tP + k * 8, dv, IDESC_PV, (j | k) != 0);  // 16 keys = 8 packed columns
         }
         umma_commit(o_full);
-        umma_commit(v_empty(vs));
+        if (j + KVS < n_kt) load_k(j + KVS);
+        if (j >= 1 && j + 2 < n_kt) load_v(j + 2);
       }
     }
   } else {
