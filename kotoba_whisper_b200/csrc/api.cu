@@ -23,6 +23,9 @@ void set_error(const char* fmt, ...) {
 }
 
 // kernels defined in the other translation units
+#ifdef KW_LOGMEL_TIMING
+void logmel_debug_dump();
+#endif
 int logmel_launch(const float* audio, const int32_t* lens, int B, int n_samples, int n_mels, float* out,
                   float* clip_max, cudaStream_t st);
 void mel_filterbank_f64(int n_mels, std::vector<double>& fb);
@@ -191,6 +194,12 @@ int kw_logmel(const float* audio, const int32_t* lens, int32_t B, int32_t n_samp
 }
 
 int kw_mel_filterbank(int32_t n_mels, double* out_host) {
+#ifdef KW_LOGMEL_TIMING
+  if (n_mels < 0) {  // debug build: dump + reset the log-mel phase counters
+    kw::logmel_debug_dump();
+    return KW_OK;
+  }
+#endif
   KW_REQUIRE(n_mels > 0 && n_mels <= 128 && out_host, "kw_mel_filterbank: bad arguments");
   std::vector<double> fb;
   mel_filterbank_f64(n_mels, fb);

@@ -31,10 +31,13 @@ constexpr int NTHREADS = TPF * FPI;
 constexpr int NSAMP = HOP * (FT - 1) + NFFT;  // samples staged per CTA
 constexpr int MAX_TAPS = 16, MAX_MELS = 128;
 
-struct MelBankDev {
-  int start[MAX_MELS];
-  int count[MAX_MELS];
-  double w[MAX_MELS][MAX_TAPS];
+constexpr int MAX_TOTAL_TAPS = 512;  // non-zeros of the whole filterbank (every bin feeds <= 2 filters: ~2 * 201)
+struct MelBankDev {          // compact CSR: filter m = taps [off[m], off[m] + count[m]) over bins start[m] ...
+  short start[MAX_MELS];
+  short count[MAX_MELS];
+  short off[MAX_MELS];
+  short total;
+  double w[MAX_TOTAL_TAPS];
 };
 
 struct LogmelTables {
@@ -107,6 +110,41 @@ __device__ __forceinline__ void stockham_pass(const double2* __restrict__ in, do
   }
 }
 
+#ifdef KW_LOGMEL_TIMING
+// debug build only: per-phase cycle sums (thread 0 of every CTA); read with kw_mel_filterbank(-1, out8)
+__device__ unsigned long long g_lm_dbg[8];
+#define LM_T(i)                                   \
+  do {                                            \
+    if (threadIdx.x == 0) {                       \
+      const long long now_ = clock64();           \
+      dbg_acc[i] += now_ - dbg_t;                 \
+      dbg_t = now_;                               \
+    }                                             \
+  } while (0)
+#else
+#define LM_T(i)
+#endif
+
+// First pass (radix 5, no twiddles) fused with the windowing: point n of the packed 200-point sequence is
+// (x[2n] w[2n], x[2n+1] w[2n+1]), read straight from the staged samples instead of a separately written complex buffer.
+__device__ __forceinline__ void stockham_first_pass(const float* __restrict__ x, const double* __restrict__ win,
+                                                    double2* __restrict__ out, int lt) {
+  constexpr int R = 5, NB = NC / R;
+  for (int j = lt; j < NB; j += TPF) {
+    double2 v[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int n = j + i * NB;
+      const float2 s2 = *reinterpret_cast<const float2*>(x + 2 * n);
+      const double2 w2 = *reinterpret_cast<const double2*>(win + 2 * n);
+      v[i] = make_double2((double)s2.x * w2.x, (double)s2.y * w2.y);
+    }
+    dft5(v);
+#pragma unroll
+    for (int i = 0; i < R; ++i) out[j * R + i] = v[i];
+  }
+}
+
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
   if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
@@ -129,6 +167,10 @@ logmel_stft_kernel(const float* __restrict__ audio, const int* __restrict__ lens
   float* s_samp = reinterpret_cast<float*>(s_fft + FPI * 2 * NC);            // NSAMP
   float* s_tile = s_samp + NSAMP;                                            // n_mels * (FT + 1)
   __shared__ float s_wmax[NTHREADS / 32];
+  // The filterbank (~400 taps, 3 KB) lives in shared memory: fetched from global / L1 inside the dependent tap loop it
+  // made the mel stage 42 % of the kernel (KW_LOGMEL_TIMING build).
+  __shared__ double s_bw[MAX_TOTAL_TAPS];
+  __shared__ short s_bstart[MAX_MELS], s_bcount[MAX_MELS], s_boff[MAX_MELS];
 
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FT;
@@ -136,9 +178,18 @@ logmel_stft_kernel(const float* __restrict__ audio, const int* __restrict__ lens
   const int len = lens ? min(lens[b], n_samples) : n_samples;
   const float* clip = audio + (size_t)b * n_samples;
 
+#ifdef KW_LOGMEL_TIMING
+  long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbg_t = clock64();
+#endif
   for (int i = tid; i < NFFT; i += NTHREADS) s_window[i] = tables->window[i];
   for (int i = tid; i < NC; i += NTHREADS) s_tw200[i] = tables->tw200[i];
   for (int i = tid; i < NBIN; i += NTHREADS) s_tw400[i] = tables->tw400[i];
+  for (int i = tid; i < bank->total; i += NTHREADS) s_bw[i] = bank->w[i];
+  for (int i = tid; i < n_mels; i += NTHREADS) {
+    s_bstart[i] = bank->start[i];
+    s_bcount[i] = bank->count[i];
+    s_boff[i] = bank->off[i];
+  }
 
   // stage samples [160*t0 - 200, 160*t0 - 200 + NSAMP) with reflection about 0 and n_samples-1 (no edge repeat)
   const int s_begin = HOP * t0 - NFFT / 2;
@@ -155,6 +206,7 @@ logmel_stft_kernel(const float* __restrict__ audio, const int* __restrict__ lens
     }
   }
   __syncthreads();
+  LM_T(0);
 
   const int slot = tid / TPF, lt = tid % TPF;
   double2* bufA = s_fft + slot * 2 * NC;
@@ -164,15 +216,15 @@ logmel_stft_kernel(const float* __restrict__ audio, const int* __restrict__ lens
   for (int it = 0; it < FT / FPI; ++it) {
     const int f = it * FPI + slot;  // frame within the tile
     const float* x = s_samp + HOP * f;
-    for (int n = lt; n < NC; n += TPF)
-      bufA[n] = make_double2((double)x[2 * n] * s_window[2 * n], (double)x[2 * n + 1] * s_window[2 * n + 1]);
+    stockham_first_pass(x, s_window, bufB, lt);
     __syncthreads();
-    stockham_pass<5, 1>(bufA, bufB, s_tw200, lt);
-    __syncthreads();
+    LM_T(2);
     stockham_pass<5, 5>(bufB, bufA, s_tw200, lt);
     __syncthreads();
+    LM_T(3);
     stockham_pass<8, 25>(bufA, bufB, s_tw200, lt);
     __syncthreads();
+    LM_T(4);
     // real-input fold: X[k] = (Z[k] + conj Z[200-k])/2 - i/2 e^{-2 pi i k/400} (Z[k] - conj Z[200-k]); power -> bufA
     double* pw = reinterpret_cast<double*>(bufA);
     for (int k = lt; k < NBIN; k += TPF) {
@@ -185,15 +237,25 @@ logmel_stft_kernel(const float* __restrict__ audio, const int* __restrict__ lens
       pw[k] = X.x * X.x + X.y * X.y;
     }
     __syncthreads();
+    LM_T(5);
     for (int m = lt; m < n_mels; m += TPF) {
-      const int st = bank->start[m], cnt = bank->count[m];
-      double acc = 0.0;
-      for (int j = 0; j < cnt; ++j) acc += bank->w[m][j] * pw[st + j];
-      float lv = log10f(fmaxf((float)acc, 1e-10f));
+      const int cnt = s_bcount[m];
+      const double* w = s_bw + s_boff[m];
+      const double* x = pw + s_bstart[m];
+      double a0 = 0.0, a1 = 0.0;  // two independent chains: the loop is latency-, not throughput-bound
+      int j = 0;
+      for (; j + 1 < cnt; j += 2) {
+        a0 = fma(w[j], x[j], a0);
+        a1 = fma(w[j + 1], x[j + 1], a1);
+      }
+      if (j < cnt) a0 = fma(w[j], x[j], a0);
+      // lg2.approx: absolute error < 2^-22 in log2, i.e. < 2e-8 in the normalised output (bar: 1e-5)
+      float lv = __log2f(fmaxf((float)(a0 + a1), 1e-10f)) * 0.30102999566398119521f;
       s_tile[m * (FT + 1) + f] = lv;
       if (t0 + f < n_frames) local_max = fmaxf(local_max, lv);
     }
     __syncthreads();
+    LM_T(6);
   }
 
   float* dst = out + (size_t)b * n_mels * n_frames;
@@ -209,7 +271,26 @@ logmel_stft_kernel(const float* __restrict__ audio, const int* __restrict__ lens
     for (int i = 1; i < NTHREADS / 32; ++i) mx = fmaxf(mx, s_wmax[i]);
     atomic_max_float(clip_max + b, mx);
   }
+  LM_T(7);
+#ifdef KW_LOGMEL_TIMING
+  if (tid == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_lm_dbg[i], (unsigned long long)dbg_acc[i]);
+#endif
 }
+
+#ifdef KW_LOGMEL_TIMING
+void logmel_debug_dump() {
+  unsigned long long h[8], z[8] = {0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(h, g_lm_dbg, sizeof(h));
+  const char* nm[8] = {"0 tables + sample staging", "1 window -> complex", "2 radix-5 pass", "3 radix-5 pass (twiddled)",
+                       "4 radix-8 pass", "5 fold + power", "6 mel + log", "7 tile store + max"};
+  double tot = 0;
+  for (int i = 0; i < 8; ++i) tot += (double)h[i];
+  for (int i = 0; i < 8; ++i) fprintf(stderr, "  logmel phase %-28s %5.1f %%\n", nm[i], 100.0 * h[i] / tot);
+  cudaMemcpyToSymbol(g_lm_dbg, z, sizeof(z));
+}
+#endif
 
 // y = (max(x, clipmax - 8) + 4) / 4 in place; per_clip = n_mels * n_frames (multiple of 4)
 __global__ void logmel_finalize_kernel(float* __restrict__ x, const float* __restrict__ clip_max, int per_clip4,
@@ -277,6 +358,7 @@ static int get_tables(int n_mels, const LogmelTables** tables, const MelBankDev*
     mel_filterbank_f64(n_mels, fb);
     std::vector<MelBankDev> h(1);
     memset(h.data(), 0, sizeof(MelBankDev));
+    int total = 0;
     for (int m = 0; m < n_mels; ++m) {
       int first = -1, last = -1;
       for (int k = 0; k < NBIN; ++k)
@@ -285,11 +367,14 @@ static int get_tables(int n_mels, const LogmelTables** tables, const MelBankDev*
           last = k;
         }
       if (first < 0) { first = 0; last = -1; }
-      KW_REQUIRE(last - first + 1 <= MAX_TAPS, "mel filter %d spans %d bins (> %d)", m, last - first + 1, MAX_TAPS);
-      h[0].start[m] = first;
-      h[0].count[m] = last - first + 1;
-      for (int k = first; k <= last; ++k) h[0].w[m][k - first] = fb[(size_t)k * n_mels + m];
+      const int cnt = last - first + 1;
+      KW_REQUIRE(total + cnt <= MAX_TOTAL_TAPS, "mel filterbank has more than %d taps", MAX_TOTAL_TAPS);
+      h[0].start[m] = (short)first;
+      h[0].count[m] = (short)cnt;
+      h[0].off[m] = (short)total;
+      for (int k = first; k <= last; ++k) h[0].w[total++] = fb[(size_t)k * n_mels + m];
     }
+    h[0].total = (short)total;
     KW_CUDA_OK(cudaMalloc(&g_lm.bank[n_mels], sizeof(MelBankDev)));
     KW_CUDA_OK(cudaMemcpy(g_lm.bank[n_mels], h.data(), sizeof(MelBankDev), cudaMemcpyHostToDevice));
   }
