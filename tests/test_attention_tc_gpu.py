@@ -59,7 +59,10 @@ def test_attention_tc_p_path_only():
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk", [(1, 1, 128, 128), (1, 2, 128, 384), (2, 3, 100, 37), (1, 2, 300, 1500),
-                                       (1, 20, 1500, 1500), (3, 20, 1500, 1500)])
+                                       (1, 20, 1500, 1500), (3, 20, 1500, 1500),
+                                       # key-tile edges of the 3-slot K/V ring: exactly one tile, one key into the second
+                                       # tile, 4 tiles (first slot reuse), a single query row
+                                       (1, 1, 64, 64), (2, 2, 130, 65), (1, 3, 257, 200), (2, 1, 1, 449)])
 def test_attention_tc_matches_torch(B, H, Tq, Tk):
     torch.manual_seed(B * 1000 + Tq + Tk)
     d = H * 64
@@ -74,3 +77,21 @@ def test_attention_tc_matches_torch(B, H, Tq, Tk):
     assert err <= 1.5e-2 * scale, f"max err {err} (scale {scale})"
     simt = _attn(q, k, v, B, H, Tq, Tk, impl=1)
     assert (out.float() - simt.float()).abs().max().item() <= 2.5e-2 * scale
+
+
+def test_attention_tc_running_max_moves_every_tile():
+    """Scores that keep growing along the key axis: the lazy running maximum (moved only when a tile exceeds it by 2^8)
+    and the O rescale in tensor memory are exercised on every tile, not just the first."""
+    torch.manual_seed(11)
+    B, H, Tq, Tk = 2, 2, 256, 640
+    d = H * 64
+    q = (torch.randn(B, Tq, d, device="cuda") * 0.3)
+    k = torch.randn(B, Tk, d, device="cuda") * 0.3
+    ramp = torch.linspace(0.0, 6.0, Tk, device="cuda")[None, :, None]      # |k| grows -> later tiles dominate
+    k = k + ramp * torch.sign(q.mean(dim=1, keepdim=True))
+    v = torch.randn(B, Tk, d, device="cuda")
+    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    out = _attn(q, k, v, B, H, Tq, Tk)
+    ref = _ref(q, k, v, B, H, Tq, Tk)
+    scale = max(1.0, ref.abs().max().item())
+    assert (out.float() - ref).abs().max().item() <= 1.5e-2 * scale
