@@ -486,7 +486,7 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 // same item order (EPI_RESID, V = 4 only).
 template <int R, int V, int EPI, bool OUT_BF16>
 __device__ __forceinline__ void skinny_store(const Params& p, const float* stage, int n_slots, int n0, int tid,
-                                             const float4* res) {
+                                             const float4* res, const float4& bias4) {
   constexpr int GROUPS = R / V, ITEMS = sk::BN * GROUPS, PER = ITEMS / (SK_EPI_WARPS * 32);
   constexpr int UNROLL = PER <= 4 ? PER : 4;  // res[i] (PER = 4) needs the full unroll; longer loops keep registers down
 #pragma unroll UNROLL
@@ -500,7 +500,9 @@ __device__ __forceinline__ void skinny_store(const Params& p, const float* stage
 #pragma unroll
       for (int e = 0; e < V; ++e) v[e] += stage[(sl * sk::BN + row) * R + f + e];
     }
-    if (p.bias) {
+    if (V == 4 && R == 32) {  // every item of a thread covers the same 4 features: one bias group, requested up front
+      v[0] += bias4.x; v[1] += bias4.y; v[V - 2] += bias4.z; v[V - 1] += bias4.w;
+    } else if (p.bias) {
 #pragma unroll
       for (int e = 0; e < V; ++e) v[e] += __ldg(p.bias + n + e);
     }
@@ -531,14 +533,14 @@ __device__ __forceinline__ void skinny_store(const Params& p, const float* stage
 
 template <int R, int V>
 __device__ __forceinline__ void skinny_store_dispatch(const Params& p, const float* stage, int n_slots, int n0, int tid,
-                                                      const float4* res) {
+                                                      const float4* res, const float4& bias4) {
   if (p.out_bf16) {
-    if (p.epi == EPI_GELU) skinny_store<R, V, EPI_GELU, true>(p, stage, n_slots, n0, tid, res);
-    else skinny_store<R, V, EPI_STORE, true>(p, stage, n_slots, n0, tid, res);
+    if (p.epi == EPI_GELU) skinny_store<R, V, EPI_GELU, true>(p, stage, n_slots, n0, tid, res, bias4);
+    else skinny_store<R, V, EPI_STORE, true>(p, stage, n_slots, n0, tid, res, bias4);
   } else {
-    if (p.epi == EPI_GELU) skinny_store<R, V, EPI_GELU, false>(p, stage, n_slots, n0, tid, res);
-    else if (p.epi == EPI_RESID) skinny_store<R, V, EPI_RESID, false>(p, stage, n_slots, n0, tid, res);
-    else skinny_store<R, V, EPI_STORE, false>(p, stage, n_slots, n0, tid, res);
+    if (p.epi == EPI_GELU) skinny_store<R, V, EPI_GELU, false>(p, stage, n_slots, n0, tid, res, bias4);
+    else if (p.epi == EPI_RESID) skinny_store<R, V, EPI_RESID, false>(p, stage, n_slots, n0, tid, res, bias4);
+    else skinny_store<R, V, EPI_STORE, false>(p, stage, n_slots, n0, tid, res, bias4);
   }
 }
 
@@ -684,6 +686,9 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                        : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);  // R = 32, vec = 4: this thread's only bias group (idx % 8 = tid % 8)
+      if (R == 32 && vec == 4 && rank == 0 && p.bias && t * BM + (tid % 8) * 4 < p.N)
+        bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + t * BM + (tid % 8) * 4));
       mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
       if (threadIdx.x == 0 && tcount == 0) stamp(8);
       tc_fence_after();
@@ -711,9 +716,9 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       mbar_arrive(tempty_bar(as));
       if (S == 1) {
         asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer complete
-        if (vec == 4) skinny_store_dispatch<R, 4>(p, out_stage, 1, t * BM, tid, res);
-        else if (vec == 2) skinny_store_dispatch<R, 2>(p, out_stage, 1, t * BM, tid, res);
-        else skinny_store_dispatch<R, 1>(p, out_stage, 1, t * BM, tid, res);
+        if (vec == 4) skinny_store_dispatch<R, 4>(p, out_stage, 1, t * BM, tid, res, bias4);
+        else if (vec == 2) skinny_store_dispatch<R, 2>(p, out_stage, 1, t * BM, tid, res, bias4);
+        else skinny_store_dispatch<R, 1>(p, out_stage, 1, t * BM, tid, res, bias4);
         if (tcount + 1 < my_tiles) asm volatile("bar.sync 1, 128;" ::: "memory");  // buffer free for the next tile
         if (threadIdx.x == 0) stamp(5 + (tcount == 0 ? 0 : 1));
       } else {
@@ -722,9 +727,9 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         if (rank == 0) {
           asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
           if (threadIdx.x == 0) stamp(10);
-          if (vec == 4) skinny_store_dispatch<R, 4>(p, out_stage, S, t * BM, tid, res);
-          else if (vec == 2) skinny_store_dispatch<R, 2>(p, out_stage, S, t * BM, tid, res);
-          else skinny_store_dispatch<R, 1>(p, out_stage, S, t * BM, tid, res);
+          if (vec == 4) skinny_store_dispatch<R, 4>(p, out_stage, S, t * BM, tid, res, bias4);
+          else if (vec == 2) skinny_store_dispatch<R, 2>(p, out_stage, S, t * BM, tid, res, bias4);
+          else skinny_store_dispatch<R, 1>(p, out_stage, S, t * BM, tid, res, bias4);
           if (threadIdx.x == 0) stamp(5);
         }
       }
@@ -808,7 +813,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     // widest store the output layout allows: V features of one batch row per 16 / 8 / 4-byte (fp32) store
     const int esz = g.out_type == KW_BF16 ? 2 : 4;
     int vec = 1;
-    if (g.N % 4 == 0 && g.ldo % 4 == 0 && ((uintptr_t)g.out % (4 * esz)) == 0) vec = 4;
+    if (g.N % 4 == 0 && g.ldo % 4 == 0 && ((uintptr_t)g.out % (4 * esz)) == 0 && ((uintptr_t)g.bias % 16) == 0) vec = 4;
     else if (g.N % 2 == 0 && g.ldo % 2 == 0 && ((uintptr_t)g.out % (2 * esz)) == 0) vec = 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
