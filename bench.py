@@ -67,15 +67,25 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.proc, self.lines, self.index = None, [], index
+        self.proc, self.lines, self.index, self.t_begin = None, [], index, 0.0
 
     def start(self):
+        """Launch the poller.  Called BEFORE the warm-up: nvidia-smi takes ~1 s to initialise (it enumerates every GPU of
+        the box under a driver lock), which must not land inside the timed region; only samples that arrive after
+        `mark_begin()` are used."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+
+            def reader():
+                for l in self.proc.stdout:
+                    self.lines.append((time.monotonic(), l))
+            threading.Thread(target=reader, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def mark_begin(self):
+        self.t_begin = time.monotonic()
 
     def stop(self):
         if self.proc is None:
@@ -87,7 +97,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for t_line, l in self.lines:
+            if t_line < self.t_begin:
+                continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 6:
                 continue
@@ -219,6 +231,9 @@ def ours(args, rank: int, world: int, local_rank: int):
             ms = float(t.item())
         return ms, out
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_resident()
     # Timed region: only the dominant kernel category (encoder GEMMs) carries CUDA-event pairs; the other categories
@@ -228,9 +243,7 @@ def ours(args, rank: int, world: int, local_rank: int):
         _lib.profile_read(c, reset=True)
     lib.kw_profile_enable(1 << _lib.PROF_ENC_GEMM)
     lib.kw_launch_count(1)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark_begin()
     ms, ids = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = int(lib.kw_launch_count(0))
