@@ -133,6 +133,7 @@ struct kw_model {
   void* xkv = nullptr;  // [L][B*S][2d]
   int* finished = nullptr;
   int* finished_host = nullptr;  // pinned
+  cudaEvent_t finished_copied = nullptr;
   int enc_B = 0;
 };
 
@@ -276,6 +277,7 @@ void kw_model_destroy(kw_model* m) {
   if (!m) return;
   cudaFree(m->pool);
   if (m->finished_host) cudaFreeHost(m->finished_host);
+  if (m->finished_copied) cudaEventDestroy(m->finished_copied);
   delete m;
 }
 
@@ -443,20 +445,32 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
   KW_LAUNCH_OK();
   ++g_launches;
   KW_TRY(kw_cross_kv(m, B, stream));
-  int steps = 0;
+  // The all-rows-finished poll must not drain the stream (the host would then have to refill the launch queue while
+  // the GPU idles, and the first kernels after the gap lose their programmatic-launch overlap): the flags are copied out
+  // behind an event and looked at POLL_LAG positions later, when the copy has long completed but the GPU still has
+  // those positions queued.  Positions computed after every row finished only write pad tokens over pad tokens.
+  constexpr int POLL_LAG = 4;
+  if (!m->finished_copied) KW_CUDA_OK(cudaEventCreateWithFlags(&m->finished_copied, cudaEventDisableTiming));
+  int steps = 0, pending_since = -1;
   for (int pos = 0; pos + 1 < max_length; ++pos) {
     const int sample = pos >= n_prompt - 1;
     KW_TRY(kw_decode_step(m, tokens, max_length, B, pos, n_prompt, sample, return_timestamps, m->finished, nullptr, stream));
     ++steps;
     const int generated = pos + 2 - n_prompt;  // tokens sampled so far
-    if (check_every > 0 && sample && generated % check_every == 0 && pos + 2 < max_length) {
+    if (check_every > 0 && sample && generated % check_every == 0 && pos + 2 < max_length && pending_since < 0) {
       KW_CUDA_OK(cudaMemcpyAsync(m->finished_host, m->finished, B * sizeof(int), cudaMemcpyDeviceToHost, st));
-      KW_CUDA_OK(cudaStreamSynchronize(st));
+      KW_CUDA_OK(cudaEventRecord(m->finished_copied, st));
+      pending_since = pos;
+    }
+    if (pending_since >= 0 && pos >= pending_since + POLL_LAG) {
+      KW_CUDA_OK(cudaEventSynchronize(m->finished_copied));
+      pending_since = -1;
       bool all = true;
       for (int b = 0; b < B; ++b) all = all && m->finished_host[b];
       if (all) break;
     }
   }
+  if (pending_since >= 0) KW_CUDA_OK(cudaEventSynchronize(m->finished_copied));  // finished_host is reused by the next pass
   return steps;
 }
 

@@ -459,15 +459,16 @@ constexpr int MAX_SPLIT = 4;
 // accumulator rows are never read back.
 template <int R> struct Cfg {
   static constexpr int A_BYTES = R * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = R == 32 ? 12 : 8;
+  static constexpr int STAGES = R == 32 ? 12 : R == 40 ? 10 : 8;
   // k-block slots that share one full / empty mbarrier pair (one wait + fence per group on the MMA-issuing thread)
-  static constexpr int GROUP = R == 32 ? 4 : 2;
+  static constexpr int GROUP = R == 32 ? 4 : 2;  // (STAGES is a multiple of GROUP)
   static constexpr int RING = STAGES * STAGE_BYTES + (BM - R) * BK * 2;  // + tail the M = 128 read of the last stage may touch
   static constexpr int SLOTS = R == 32 ? MAX_SPLIT : 1;                  // split-K partial slots (R = 32 only)
   static constexpr int OUT_STAGE = SLOTS * BN * R * 4;                   // [slot][batch row][feature] fp32
   static constexpr size_t SMEM_BYTES = 1024 + (size_t)RING + 512 + OUT_STAGE;
 };
-static_assert(Cfg<32>::SMEM_BYTES <= 232448 && Cfg<128>::SMEM_BYTES <= 232448, "skinny GEMM smem budget");
+static_assert(Cfg<32>::SMEM_BYTES <= 232448 && Cfg<40>::SMEM_BYTES <= 232448 && Cfg<128>::SMEM_BYTES <= 232448,
+              "skinny GEMM smem budget");
 constexpr int TMEM_COLS = 128;
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
 }  // namespace sk
@@ -702,6 +703,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           tmem_ld32(taddr + c * 32, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           const int col = warp * 32 + lane;  // feature inside the tile
+          if (col >= R) continue;            // R = 40: lanes 8..31 of warp 1 sit on garbage accumulator rows
           if (S > 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) st_cluster_f32(slot_remote + ((c * 32 + j) * R + col) * 4, __uint_as_float(r[j]));
@@ -781,6 +783,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sk::Cfg<32>::SMEM_BYTES));
+    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sk::Cfg<40>::SMEM_BYTES));
     KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sk::Cfg<128>::SMEM_BYTES));
     attr = true;
@@ -792,7 +796,10 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.epi = g.epi; p.out_bf16 = g.out_type == KW_BF16;
   CUtensorMap tmA, tmB;
   if (g.M <= sk::BN && g.epi != EPI_GELU_POS) {  // decode-time shape: weights stream through the 128-row dimension
-    const int R = g.N <= 8192 ? 32 : 128;  // small projections: 32 weight rows per CTA tile -> 4x the CTAs in flight
+    // small projections: 32 weight rows per CTA tile -> 4x the CTAs in flight; 40 rows when 32-row tiles would spill
+    // into a second wave by a few tiles (fc1: N = 5120 -> 160 tiles on 148 SMs took 15.3 us, 128 tiles of 40 rows one wave)
+    int R = g.N <= 8192 ? 32 : 128;
+    if (R == 32 && ceil_div(g.N, 32) > n_sm && ceil_div(g.N, 40) <= n_sm) R = 40;
     int rc = make_map(&tmB, g.W, g.N, g.K, g.K, R);
     if (rc) return rc;
     if ((rc = make_map(&tmA, g.A, g.M, g.K, g.lda, sk::BN))) return rc;
@@ -819,7 +826,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(split > 1 ? tiles * split : std::min(tiles, n_sm));
     cfg.blockDim = dim3(SK_THREADS);
-    cfg.dynamicSmemBytes = R == 32 ? sk::Cfg<32>::SMEM_BYTES : sk::Cfg<128>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = R == 32 ? sk::Cfg<32>::SMEM_BYTES : R == 40 ? sk::Cfg<40>::SMEM_BYTES : sk::Cfg<128>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attrs[2];
     int na = 0;
@@ -838,6 +845,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     cfg.attrs = attrs;
     cfg.numAttrs = na;
     if (R == 32) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<32>, tmB, tmA, p, vec));
+    else if (R == 40) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<40>, tmB, tmA, p, vec));
     else KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<128>, tmB, tmA, p, vec));
     KW_LAUNCH_OK();
     ++g_launches;
