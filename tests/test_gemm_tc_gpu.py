@@ -27,7 +27,9 @@ SHAPES = [(128, 256, 64), (256, 512, 128), (100, 128, 128), (1500, 1280, 1280), 
           (64, 3840, 1280), (64, 1280, 5120), (4, 51866, 1280), (1, 1280, 1280), (33, 5120, 1280), (64, 128, 128),
           (17, 200, 64),
           # cluster split-K (N <= ~1500: tiles x split <= 148 CTAs): uneven k-ranges, 2- and 3-way, 8 / 4-byte store paths
-          (64, 1280, 1280), (5, 1000, 832), (7, 1282, 512), (3, 333, 1280), (40, 1536, 1024)]
+          (64, 1280, 1280), (5, 1000, 832), (7, 1282, 512), (3, 333, 1280), (40, 1536, 1024),
+          # 40-row tiles (32-row tiles would need a second wave on 148 SMs): exact and ragged last tile, 8 / 4-byte stores
+          (64, 5120, 1280), (7, 5040, 256), (5, 4762, 128)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
