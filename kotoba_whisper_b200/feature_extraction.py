@@ -7,6 +7,7 @@ same `__call__` keywords, same `input_features` / `attention_mask` outputs, same
 """
 from __future__ import annotations
 
+import threading
 from typing import List, Optional, Sequence, Union
 
 import numpy as np
@@ -88,6 +89,7 @@ class WhisperFeatureExtractorB200:
         self._pinned: List[Optional[torch.Tensor]] = [None, None]
         self._copy_done: List[Optional[torch.cuda.Event]] = [None, None]
         self._side: Optional[torch.cuda.Stream] = None
+        self._stage_lock = threading.Lock()  # the two staging buffers are shared by __call__ and prefetch workers
 
     # ---- device entry: already-padded clips on the GPU ---------------------------------------------------------
     def logmel_device(self, audio: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -116,6 +118,10 @@ class WhisperFeatureExtractorB200:
         max(staging, PCIe) instead of their sum.  Two staging buffers alternate, so a `prefetch` for the next batch
         can fill one while the previous batch's copy is still draining the other."""
         B = len(clips)
+        with self._stage_lock:
+            return self._stage_and_copy_locked(clips, lens, target, dev, B)
+
+    def _stage_and_copy_locked(self, clips, lens, target: int, dev: torch.device, B: int) -> torch.Tensor:
         slot = self._slot = (getattr(self, "_slot", 1) + 1) % 2
         if self._pinned[slot] is None or self._pinned[slot].numel() < B * target:
             self._pinned[slot] = torch.empty(B * target, dtype=torch.float32).pin_memory()
