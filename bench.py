@@ -181,16 +181,17 @@ def ours(args, rank: int, world: int, local_rank: int):
     import torch.distributed as dist
     from kotoba_whisper_b200 import (WhisperB200Config, WhisperB200ForConditionalGeneration,
                                      WhisperFeatureExtractorB200, _lib)
-    from kotoba_whisper_b200.distributed import gather_token_ids
-    from kotoba_whisper_b200.random_init import random_state_dict
+    from kotoba_whisper_b200.distributed import TokenGather
+    from _hf import build_hf
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     lib = _lib.load()
     cfg = WhisperB200Config(**KOTOBA)
-    sd = random_state_dict(cfg, seed=0, device=dev)
+    # ONE state_dict for both arms: HF's own CPU initialisation under torch.manual_seed(0), shipped to
+    # the GPU — the reference arm builds the identical model (reference_arm -> build_hf(KOTOBA, seed=0)).
+    sd = {k: v.detach() for k, v in build_hf(KOTOBA, seed=0).state_dict().items()}
     model = WhisperB200ForConditionalGeneration.from_state_dict(sd, cfg, dtype=torch.bfloat16, max_batch=BATCH, device=dev)
-    del sd
     torch.cuda.empty_cache()
     fe = WhisperFeatureExtractorB200(feature_size=128, device=dev)
     audio_host = synth_audio(BATCH, seed=1000 * 1 + rank)       # seed = 1000*config + rank
@@ -198,18 +199,22 @@ def ours(args, rank: int, world: int, local_rank: int):
     clips_host = list(audio_host)
     pad = model.generation_config.pad_token_id
     stats = {}
+    # the only collective: ONE fixed-shape all_gather of [64, max_length - prompt] int32 per batch, enqueued
+    # asynchronously and read one batch later (no size exchange, no host sync between ranks inside a step)
+    gather = TokenGather(BATCH, MAX_LENGTH - 4, pad)
+    inflight = {"h": None}
 
     def step_resident():
         feats = fe.logmel_device(audio_dev)
         ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=MAX_LENGTH,
                              stats=stats)
-        return gather_token_ids(ids, pad)
+        prev, inflight["h"] = inflight["h"], gather.submit(ids)
+        return (prev or inflight["h"]).result()
 
     def step_e2e():
         feats = fe(clips_host, sampling_rate=SR, return_tensors="pt", keep_on_device=True)["input_features"]
         ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=MAX_LENGTH)
-        ids = gather_token_ids(ids, pad)
-        return ids.cpu()
+        return gather.submit(ids).result().cpu()
 
     def barrier():
         if world > 1:
@@ -253,6 +258,10 @@ def ours(args, rank: int, world: int, local_rank: int):
     ms_extra, _ = timed(step_resident, extra_steps)
     for c in (_lib.PROF_ENC_ATTN, _lib.PROF_DEC_CROSS, _lib.PROF_LOGMEL):
         prof[c] = _lib.profile_read(c, reset=True)
+    # whole decode pass (all kernels of all positions) under ONE event pair, so programmatic launch chains stay intact
+    lib.kw_profile_enable(1 << _lib.PROF_DEC_PASS)
+    ms_pass_steps, _ = timed(step_resident, extra_steps)
+    prof[_lib.PROF_DEC_PASS] = _lib.profile_read(_lib.PROF_DEC_PASS, reset=True)
     lib.kw_profile_enable(0)
     passes = stats.get("passes", 0)
 
@@ -263,7 +272,7 @@ def ours(args, rank: int, world: int, local_rank: int):
     # DataLoader workers prepare batch i+1 while the model labels batch i.  Every step's host staging, H2D copy and
     # D2H token read happen inside the timed region; only their overlap with the previous step's kernels differs.
     def run_e2e_pipelined(steps):
-        out = None
+        out, h = None, None
         pending = fe.prefetch(clips_host, sampling_rate=SR, return_tensors="pt")
         for i in range(steps):
             feats = pending.result()["input_features"]
@@ -271,8 +280,10 @@ def ours(args, rank: int, world: int, local_rank: int):
                 pending = fe.prefetch(clips_host, sampling_rate=SR, return_tensors="pt")
             ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False,
                                  max_length=MAX_LENGTH)
-            out = gather_token_ids(ids, pad).cpu()
-        return out
+            prev, h = h, gather.submit(ids)
+            if prev is not None:
+                out = prev.result().cpu()  # batch i-1's gathered ids -> host while batch i's gather is in flight
+        return h.result().cpu()
 
     run_e2e_pipelined(2)
     ms_e2e, ids_host = timed(lambda: run_e2e_pipelined(args.steps), 1)
@@ -283,6 +294,7 @@ def ours(args, rank: int, world: int, local_rank: int):
     if rank != 0:
         return
     hbm, tf_sus, tf_burst, peak_src = load_peaks()
+    NOMINAL_TF, NOMINAL_GBS = 2250.0, 8000.0  # fractions are reported against nominal peaks too
 
     def leg(cat, unit_scale, total_ms):
         t, n, work = prof[cat]
@@ -292,17 +304,51 @@ def ours(args, rank: int, world: int, local_rank: int):
     a_tf, a_n, a_share = leg(_lib.PROF_ENC_ATTN, 1e12, ms_extra)
     x_gb, x_n, x_share = leg(_lib.PROF_DEC_CROSS, 1e9, ms_extra)
     m_gb, m_n, m_share = leg(_lib.PROF_LOGMEL, 1e9, ms_extra)
+    p_gb, p_n, p_share = leg(_lib.PROF_DEC_PASS, 1e9, ms_pass_steps)
+    # ncu-measured DRAM traffic of the dominant kernel category (profiles/r2_traffic.json, written by
+    # tools/ncu_traffic.py from an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` pass of this command)
+    traffic, traffic_note = None, "no profiles/r2_traffic.json"
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("encoder_gemm_launches"):
+            traffic = tj["encoder_gemm_dram_bytes"] / tj["encoder_gemm_launches"]
+            traffic_note = f"ncu dram bytes per launch averaged over {tj['encoder_gemm_launches']} encoder GEMM launches; " \
+                           f"algorithmic operand bytes per launch {tj.get('encoder_gemm_algorithmic_bytes', 0) / tj['encoder_gemm_launches']:.3e}"
+    pass_t, pass_n, pass_work = prof[_lib.PROF_DEC_PASS]
+    positions = (MAX_LENGTH - 1) * max(pass_n, 1)
     roofline = {"kernel": "encoder GEMMs (conv stem, QKV, out, fc1, fc2)", "bound": "tensor", "achieved": g_tf,
-                "peak": tf_sus, "unit": "TFLOP/s", "frac": g_tf / tf_sus, "traffic": None, "peak_source": peak_src,
-                "launches": g_n, "share_of_step": g_share}
+                "peak": tf_sus, "unit": "TFLOP/s", "frac": g_tf / tf_sus, "frac_burst": g_tf / tf_burst,
+                "frac_nominal": g_tf / NOMINAL_TF, "traffic": traffic, "traffic_note": traffic_note,
+                "peak_source": peak_src, "launches": g_n, "share_of_step": g_share}
     extra = [
         {"kernel": "encoder self-attention", "bound": "tensor", "achieved": a_tf, "peak": tf_sus, "unit": "TFLOP/s",
-         "frac": a_tf / tf_sus, "launches": a_n, "share_of_step": a_share},
+         "frac": a_tf / tf_sus, "frac_nominal": a_tf / NOMINAL_TF, "launches": a_n, "share_of_step": a_share},
+        {"kernel": "decode step (all kernels of a decoder position, whole greedy pass under one event pair)",
+         "bound": "hbm", "achieved": p_gb, "peak": hbm, "unit": "GB/s", "frac": p_gb / hbm,
+         "frac_nominal": p_gb / NOMINAL_GBS, "passes": pass_n, "share_of_step": p_share,
+         "ms_per_position": pass_t / positions if positions else None,
+         "algorithmic_bytes_per_position": pass_work / positions if positions else None},
         {"kernel": "decode-step cross-attention", "bound": "hbm", "achieved": x_gb, "peak": hbm, "unit": "GB/s",
-         "frac": x_gb / hbm, "launches": x_n, "share_of_step": x_share},
+         "frac": x_gb / hbm, "frac_nominal": x_gb / NOMINAL_GBS, "launches": x_n, "share_of_step": x_share},
         {"kernel": "log-mel (stft+mel+log, incl. fix-up pass)", "bound": "hbm", "achieved": m_gb, "peak": hbm,
-         "unit": "GB/s", "frac": m_gb / hbm, "launches": m_n, "share_of_step": m_share},
+         "unit": "GB/s", "frac": m_gb / hbm, "frac_nominal": m_gb / NOMINAL_GBS, "launches": m_n, "share_of_step": m_share},
     ]
+    parity = None
+    if not args.no_parity:
+        # the benched run parity-checked in place: the same 64 clips and the same weights through the exact-fp32 CUDA path
+        try:
+            from kotoba_whisper_b200.parity import bf16_token_parity, rounded_state_dict
+            m32 = WhisperB200ForConditionalGeneration.from_state_dict(rounded_state_dict(sd), cfg, dtype=torch.float32,
+                                                                      max_batch=16, device=dev)
+            parity = bf16_token_parity(model, m32, fe.logmel_device(audio_dev), max_length=MAX_LENGTH)
+            for k in ("first_divergence_step", "fp32_gap_at_divergence"):
+                parity.pop(k, None)
+            parity["bar"] = "bf16: token sequences identical on >= 99 % of utterances (near-ties below tau count as identical)"
+            parity["meets_bar"] = parity["adjusted_pct"] >= 99.0
+            del m32
+        except Exception as e:
+            parity = {"error": f"{type(e).__name__}: {e}"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -323,7 +369,7 @@ def ours(args, rank: int, world: int, local_rank: int):
                     "serial_value": audio_s * args.steps / (ms_e2e_serial / 1e3),
                     "h2d_bytes_per_step": int(audio_host.nbytes) * world,
                     "d2h_bytes_per_step": int(ids_host.numel() * ids_host.element_size())},
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": launches, "clocks": clocks, "parity": parity}
     print(json.dumps(line), flush=True)
 
 
@@ -335,6 +381,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=1, help="clips per step of the bounded CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-place bf16-vs-fp32 token parity check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -130,6 +130,13 @@ const char* kw_version(void);
  * clip_max dev f32 [B] scratch (per-clip max of log10 mel), overwritten. */
 int kw_logmel(const float* audio, const int32_t* lens, int32_t B, int32_t n_samples, int32_t n_mels, float* out,
               float* clip_max, kw_stream stream);
+/* Window mode — the device-side chunker of the ASR pipeline (HF/pipelines/automatic_speech_recognition.py:61-84
+ * `chunk_iter`, called on behalf of run_speed_eval.py:76): the recording is uploaded ONCE; window w covers samples
+ * [starts[w], starts[w] + lens[w]) of it and is featurised as if it had been copied out and right-padded with zeros
+ * to n_samples (lens[w] <= n_samples; the caller guarantees starts[w] + lens[w] <= recording length).
+ * recording dev f32 [n_total]; starts dev i64 [W]; lens dev i32 [W]; out dev f32 [W, n_mels, n_samples/160]. */
+int kw_logmel_windows(const float* recording, const int64_t* starts, const int32_t* lens, int32_t W, int32_t n_samples,
+                      int32_t n_mels, float* out, float* clip_max, kw_stream stream);
 /* Slaney filterbank as the kernel uses it, float64 [201, n_mels] row-major, written to a HOST buffer (test hook). */
 int kw_mel_filterbank(int32_t n_mels, double* out_host);
 
@@ -167,6 +174,14 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
 int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
                    int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream);
 
+/* Teacher-forcing decoder forward (no KV cache) on the handle's current encoder output: all T positions at once,
+ * causal self-attention, cross-attention over the encoder K/V, proj_out — what `teacher_model(encoder_outputs=...,
+ * labels=...)` computes in the reference's distillation step (run_distillation.py:641-649; WhisperDecoder.forward,
+ * HF/models/whisper/modeling_whisper.py:734-796, 1069-1081).
+ * decoder_input_ids dev i32 [B, T] (already shifted right by the caller); logits_out dev f32 [B, T, vocab]. */
+int kw_decoder_forward(kw_model* m, const int32_t* decoder_input_ids, int32_t B, int32_t T, float* logits_out,
+                       kw_stream stream);
+
 /* ---- attention seam ------------------------------------------------------------------------------------------------
  * q,k,v dev [B, T, 3?]: strided views, element (b, t, h, e) at  ptr + b*stride_b + t*stride_t + h*64 + e ; head dim 64,
  * softmax(q k^T) v with q pre-scaled (scaling = 1.0 at modeling_whisper.py:349), no mask.  out dev [B, Tq, H*64]. */
@@ -195,7 +210,10 @@ enum {
   KW_PROF_DEC_GEMM = 3,  /* decode-step projections incl. vocab (FLOPs) */
   KW_PROF_DEC_CROSS = 4, /* decode-step cross-attention (bytes: cached K and V read once) */
   KW_PROF_LOGMEL = 5,    /* log-mel (bytes: audio in + features out) */
-  KW_PROF_NCAT = 6
+  KW_PROF_DEC_PASS = 6,  /* all decoder positions of one kw_greedy_pass under ONE event pair (bytes: per position
+                            actually run, the layer weights + vocabulary matrix + cross K/V + self K/V rows read so
+                            far) */
+  KW_PROF_NCAT = 7
 };
 void kw_profile_enable(uint32_t category_mask);
 int kw_profile_read(int32_t category, double* total_ms, int64_t* launches, double* work, int32_t reset);

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkwb200.so")
 
 KW_F32, KW_BF16 = 0, 1
-PROF_ENC_GEMM, PROF_ENC_ATTN, PROF_XKV_GEMM, PROF_DEC_GEMM, PROF_DEC_CROSS, PROF_LOGMEL = range(6)
+PROF_ENC_GEMM, PROF_ENC_ATTN, PROF_XKV_GEMM, PROF_DEC_GEMM, PROF_DEC_CROSS, PROF_LOGMEL, PROF_DEC_PASS = range(7)
 vp, i32, i64, f32p = C.c_void_p, C.c_int32, C.c_int64, C.c_void_p
 
 
@@ -47,6 +47,7 @@ SIGNATURES = {
     "kw_last_error": (C.c_char_p, []),
     "kw_version": (C.c_char_p, []),
     "kw_logmel": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    "kw_logmel_windows": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp]),
     "kw_mel_filterbank": (i32, [i32, vp]),
     "kw_model_create": (i32, [C.POINTER(kw_config), C.POINTER(kw_weights), C.POINTER(kw_token_rules), C.POINTER(vp)]),
     "kw_model_destroy": (None, [vp]),
@@ -56,6 +57,7 @@ SIGNATURES = {
     "kw_cross_kv": (i32, [vp, i32, vp]),
     "kw_decode_step": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "kw_greedy_pass": (i32, [vp, i32, C.POINTER(i32), i32, i32, i32, i32, vp, vp]),
+    "kw_decoder_forward": (i32, [vp, vp, i32, i32, vp, vp]),
     "kw_attention": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, vp]),
     "kw_linear": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
     "kw_layernorm": (i32, [vp, vp, vp, vp, i32, i32, i32, vp]),

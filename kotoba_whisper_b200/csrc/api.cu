@@ -26,8 +26,8 @@ void set_error(const char* fmt, ...) {
 #ifdef KW_LOGMEL_TIMING
 void logmel_debug_dump();
 #endif
-int logmel_launch(const float* audio, const int32_t* lens, int B, int n_samples, int n_mels, float* out,
-                  float* clip_max, cudaStream_t st);
+int logmel_launch(const float* audio, const long long* starts, const int32_t* lens, int B, int n_samples, int n_mels,
+                  float* out, float* clip_max, cudaStream_t st);
 void mel_filterbank_f64(int n_mels, std::vector<double>& fb);
 int im2col_conv1(const float* mel, void* A1, int B, int C, int Tn, kw_dtype t, cudaStream_t st);
 int im2col_conv2(const void* h0, void* A2, int B, int d, int Tin, int Tout, kw_dtype t, cudaStream_t st);
@@ -37,7 +37,9 @@ int embed(const int* tokens, int ld_tokens, int pos, const void* E, const float*
 int convert_f32_to(const float* in, void* out, size_t n, kw_dtype t, cudaStream_t st);
 int attention_simt(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk,
                    long long q_sb, long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st,
-                   kw_dtype t, cudaStream_t st);
+                   kw_dtype t, cudaStream_t st, int causal = 0);
+int embed_seq(const int* tokens, int ld_tokens, int T, const void* E, const float* P, float* x, int B, int d, int vocab,
+              kw_dtype t, cudaStream_t st);
 int attention_tc(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, long long q_sb,
                  long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st, cudaStream_t st);
 void attention_tc_debug(int lbo, int sbo, int kstep);
@@ -191,7 +193,15 @@ int kw_logmel(const float* audio, const int32_t* lens, int32_t B, int32_t n_samp
               float* clip_max, kw_stream stream) {
   KW_REQUIRE(audio && out && clip_max, "kw_logmel: null pointer");
   ProfScope ps(KW_PROF_LOGMEL, (double)B * (4.0 * n_samples + 4.0 * n_mels * (n_samples / 160)), (cudaStream_t)stream);
-  return logmel_launch(audio, lens, B, n_samples, n_mels, out, clip_max, (cudaStream_t)stream);
+  return logmel_launch(audio, nullptr, lens, B, n_samples, n_mels, out, clip_max, (cudaStream_t)stream);
+}
+
+int kw_logmel_windows(const float* recording, const int64_t* starts, const int32_t* lens, int32_t W, int32_t n_samples,
+                      int32_t n_mels, float* out, float* clip_max, kw_stream stream) {
+  KW_REQUIRE(recording && starts && lens && out && clip_max, "kw_logmel_windows: null pointer");
+  ProfScope ps(KW_PROF_LOGMEL, (double)W * (4.0 * n_samples + 4.0 * n_mels * (n_samples / 160)), (cudaStream_t)stream);
+  return logmel_launch(recording, (const long long*)starts, lens, W, n_samples, n_mels, out, clip_max,
+                       (cudaStream_t)stream);
 }
 
 int kw_mel_filterbank(int32_t n_mels, double* out_host) {
@@ -452,10 +462,19 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
   constexpr int POLL_LAG = 4;
   if (!m->finished_copied) KW_CUDA_OK(cudaEventCreateWithFlags(&m->finished_copied, cudaEventDisableTiming));
   int steps = 0, pending_since = -1;
+  // one event pair around the whole position loop (no events between the decode kernels: PDL chains stay intact);
+  // work = algorithmic bytes of the positions actually run: layer weights (wqkv, wo, wq_x, wo_x, w1, w2)
+  // + tied vocabulary matrix + cross K/V + the self K/V rows read so far
+  const double es_d = (double)esize(m->t), dd = m->cfg.d_model, Ld = m->cfg.dec_layers;
+  const double w_layer_bytes = (6.0 * dd * dd + 2.0 * dd * m->cfg.ffn_dim) * es_d;
+  double pass_bytes = 0.0;
+  ProfScope pass_scope(KW_PROF_DEC_PASS, 0.0, st);
   for (int pos = 0; pos + 1 < max_length; ++pos) {
     const int sample = pos >= n_prompt - 1;
     KW_TRY(kw_decode_step(m, tokens, max_length, B, pos, n_prompt, sample, return_timestamps, m->finished, nullptr, stream));
     ++steps;
+    pass_bytes += Ld * w_layer_bytes + (sample ? (double)m->cfg.vocab_size * dd * es_d : 0.0) +
+                  Ld * B * 2.0 * m->cfg.max_source_pos * dd * es_d + Ld * B * 2.0 * (pos + 1) * dd * es_d;
     const int generated = pos + 2 - n_prompt;  // tokens sampled so far
     if (check_every > 0 && sample && generated % check_every == 0 && pos + 2 < max_length && pending_since < 0) {
       KW_CUDA_OK(cudaMemcpyAsync(m->finished_host, m->finished, B * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -471,7 +490,58 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
     }
   }
   if (pending_since >= 0) KW_CUDA_OK(cudaEventSynchronize(m->finished_copied));  // finished_host is reused by the next pass
+  if (g_prof.mask & (1u << KW_PROF_DEC_PASS)) g_prof.work[KW_PROF_DEC_PASS] += pass_bytes;
   return steps;
+}
+
+// Teacher-forcing decoder forward over T positions at once (no cache): WhisperDecoder.forward + proj_out with
+// decoder_input_ids [B, T] (modeling_whisper.py:734-796, 449-506, 1069-1081), as run_distillation.py:641-649 calls the
+// frozen teacher.  Rows are (b, t)-major; the encoder workspaces double as decoder workspaces (B*T <= B*1500).
+int kw_decoder_forward(kw_model* m, const int32_t* decoder_input_ids, int32_t B, int32_t T, float* logits_out,
+                       kw_stream stream) {
+  KW_REQUIRE(m && decoder_input_ids && logits_out, "kw_decoder_forward: null argument");
+  KW_REQUIRE(B >= 1 && B <= m->enc_B, "kw_decoder_forward: B=%d but encoder output holds %d rows", B, m->enc_B);
+  KW_REQUIRE(T >= 1 && T <= m->cfg.max_target_pos, "kw_decoder_forward: T=%d outside [1, %d]", T, m->cfg.max_target_pos);
+  cudaStream_t st = (cudaStream_t)stream;
+  const kw_config& c = m->cfg;
+  const kw_dtype t = m->t;
+  const int d = c.d_model, S = c.max_source_pos, F = c.ffn_dim, H = c.n_heads, M = B * T;
+  const size_t es = esize(t);
+  const size_t xkv_stride = (size_t)c.max_batch * S * 2 * d * es;
+  KW_TRY(kw_cross_kv(m, B, stream));
+  KW_TRY(embed_seq(decoder_input_ids, T, T, m->w.tok_embed, m->w.dec_pos, m->x, B, d, c.vocab_size, t, st));
+  for (int l = 0; l < c.dec_layers; ++l) {
+    const kw_dec_layer_weights& w = m->dec[l];
+    KW_TRY(layernorm(m->x, w.ln1_w, w.ln1_b, m->a, M, d, t, st));
+    KW_TRY(gemm(mk(m->a, d, t, w.wqkv, t, w.bqkv, m->bufP, 3 * d, t, M, 3 * d, d, EPI_STORE), st));
+    const char* qkv = (const char*)m->bufP;
+    KW_TRY(attention_simt(qkv, qkv + d * es, qkv + 2 * d * es, m->o, B, H, T, T, (long long)T * 3 * d, 3 * d,
+                          (long long)T * 3 * d, 3 * d, (long long)T * d, d, t, st, /*causal=*/1));
+    KW_TRY(gemm(mk(m->o, d, t, w.wo, t, w.bo, m->x, d, KW_F32, M, d, d, EPI_RESID), st));
+    KW_TRY(layernorm(m->x, w.lnx_w, w.lnx_b, m->a, M, d, t, st));
+    KW_TRY(gemm(mk(m->a, d, t, w.wq_x, t, w.bq_x, m->bufP, d, t, M, d, d, EPI_STORE), st));
+    const char* xkv = (const char*)m->xkv + l * xkv_stride;
+    KW_TRY(kw_attention(m->bufP, xkv, xkv + d * es, m->o, B, H, T, S, (long long)T * d, d, (long long)S * 2 * d, 2 * d,
+                        (long long)T * d, d, t, stream));
+    KW_TRY(gemm(mk(m->o, d, t, w.wo_x, t, w.bo_x, m->x, d, KW_F32, M, d, d, EPI_RESID), st));
+    KW_TRY(layernorm(m->x, w.ln3_w, w.ln3_b, m->a, M, d, t, st));
+    KW_TRY(gemm(mk(m->a, d, t, w.w1, t, w.b1, m->bufQ, F, t, M, F, d, EPI_GELU), st));
+    KW_TRY(gemm(mk(m->bufQ, F, t, w.w2, t, w.b2, m->x, d, KW_F32, M, d, F, EPI_RESID), st));
+  }
+  KW_TRY(layernorm(m->x, m->w.dec_ln_w, m->w.dec_ln_b, m->a, M, d, t, st));
+  // proj_out over all positions.  The vocabulary (51866) is not a multiple of the wide tcgen05 kernel's 32-column
+  // granule, so the bf16 path streams it through the decode-time (weights-stationary) kernel 64 rows at a time.
+  if (t == KW_BF16 && c.vocab_size % 32 != 0 && g_gemm_impl.load() != 1) {
+    for (int r0 = 0; r0 < M; r0 += 64) {
+      const int rows = std::min(64, M - r0);
+      KW_TRY(gemm(mk((const char*)m->a + (size_t)r0 * d * es, d, t, m->w.tok_embed, t, nullptr,
+                     logits_out + (size_t)r0 * c.vocab_size, c.vocab_size, KW_F32, rows, c.vocab_size, d, EPI_STORE), st));
+    }
+  } else {
+    KW_TRY(gemm(mk(m->a, d, t, m->w.tok_embed, t, nullptr, logits_out, c.vocab_size, KW_F32, M, c.vocab_size, d,
+                   EPI_STORE), st));
+  }
+  return KW_OK;
 }
 
 int kw_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tq, int32_t Tk,

@@ -30,7 +30,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ out, int Tq,
                  int Tk, long long q_sb, long long q_st, long long kv_sb, long long kv_st, long long o_sb,
-                 long long o_st) {
+                 long long o_st, int causal) {
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                      // [64][68]
   float* Ks = Qs + AT_BQ * AT_LD;      // [64][68]
@@ -60,7 +60,10 @@ attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
     o_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
-  for (int k0 = 0; k0 < Tk; k0 += AT_BK) {
+  // causal (teacher-forcing decoder self-attention, create_causal_mask at modeling_whisper.py:766-772): query r sees
+  // keys 0..r; key tiles entirely above the diagonal of this query tile are skipped
+  const int k_end = causal ? min(Tk, q0 + AT_BQ) : Tk;
+  for (int k0 = 0; k0 < k_end; k0 += AT_BK) {
     __syncthreads();  // previous tile's Ks/Vs/Ps fully consumed (also covers the Qs fill)
     for (int i = tid; i < AT_BK * (HD / 4); i += 256) {
       int r = i / (HD / 4), c = (i % (HD / 4)) * 4;
@@ -102,12 +105,12 @@ attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (k0 + tx + 16 * j >= Tk) s[i][j] = -INFINITY;
+        if (k0 + tx + 16 * j >= Tk || (causal && k0 + tx + 16 * j > q0 + ty + 16 * i)) s[i][j] = -INFINITY;
         mx = fmaxf(mx, s[i][j]);
       }
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float m_new = fmaxf(m_run[i], mx);  // finite: every tile has >= 1 valid key
+      const float m_new = fmaxf(m_run[i], mx);  // finite: tile 0 holds key 0, visible to every query
       const float corr = exp_t<T>(m_run[i] - m_new);
       float rs = 0.0f;
 #pragma unroll
@@ -158,7 +161,7 @@ attn_simt_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __re
 
 int attention_simt(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk,
                    long long q_sb, long long q_st, long long kv_sb, long long kv_st, long long o_sb, long long o_st,
-                   kw_dtype t, cudaStream_t st) {
+                   kw_dtype t, cudaStream_t st, int causal) {
   KW_REQUIRE(B > 0 && H > 0 && Tq > 0 && Tk > 0, "attention: empty problem");
   KW_REQUIRE(q_st % 4 == 0 && kv_st % 4 == 0 && o_st % 4 == 0 && q_sb % 4 == 0 && kv_sb % 4 == 0 && o_sb % 4 == 0,
              "attention: strides must be multiples of 4 elements");
@@ -172,10 +175,10 @@ int attention_simt(const void* q, const void* k, const void* v, void* out, int B
   dim3 grid(ceil_div(Tq, AT_BQ), H, B);
   if (t == KW_BF16)
     attn_simt_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, Tq, Tk,
-                                                    q_sb, q_st, kv_sb, kv_st, o_sb, o_st);
+                                                    q_sb, q_st, kv_sb, kv_st, o_sb, o_st, causal);
   else
     attn_simt_kernel<float><<<grid, 256, smem, st>>>((const float*)q, (const float*)k, (const float*)v, (float*)out,
-                                                     Tq, Tk, q_sb, q_st, kv_sb, kv_st, o_sb, o_st);
+                                                     Tq, Tk, q_sb, q_st, kv_sb, kv_st, o_sb, o_st, causal);
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

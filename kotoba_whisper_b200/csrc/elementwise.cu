@@ -134,6 +134,23 @@ __global__ void __launch_bounds__(128) embed_kernel(const int* __restrict__ toke
   }
 }
 
+// teacher-forcing variant: x[(b, t)] = E[tokens[b, t]] + P[t] for t < T
+template <typename W>
+__global__ void __launch_bounds__(128) embed_seq_kernel(const int* __restrict__ tokens, int ld_tokens, int T,
+                                                        const W* __restrict__ E, const float* __restrict__ P,
+                                                        float* __restrict__ x, int d, int vocab) {
+  const int b = blockIdx.x / T, t = blockIdx.x % T;
+  int tok = tokens[(size_t)b * ld_tokens + t];
+  tok = min(max(tok, 0), vocab - 1);
+  const W* e = E + (size_t)tok * d;
+  const float* p = P + (size_t)t * d;
+  float* xr = x + (size_t)blockIdx.x * d;
+  for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
+    float4 a = ld4(e + c), q = *reinterpret_cast<const float4*>(p + c);
+    *reinterpret_cast<float4*>(xr + c) = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,6 +207,15 @@ int embed(const int* tokens, int ld_tokens, int pos, const void* E, const float*
     KW_CUDA_OK(launch_pdl(PDL_EMBED, embed_kernel<bf16>, dim3(B), dim3(128), 0, st, tokens, ld_tokens, pos, (const bf16*)E, P, x, d, vocab));
   else
     KW_CUDA_OK(launch_pdl(PDL_EMBED, embed_kernel<float>, dim3(B), dim3(128), 0, st, tokens, ld_tokens, pos, (const float*)E, P, x, d, vocab));
+  KW_LAUNCH_OK();
+  ++g_launches;
+  return KW_OK;
+}
+
+int embed_seq(const int* tokens, int ld_tokens, int T, const void* E, const float* P, float* x, int B, int d, int vocab,
+              kw_dtype t, cudaStream_t st) {
+  if (t == KW_BF16) embed_seq_kernel<bf16><<<B * T, 128, 0, st>>>(tokens, ld_tokens, T, (const bf16*)E, P, x, d, vocab);
+  else embed_seq_kernel<float><<<B * T, 128, 0, st>>>(tokens, ld_tokens, T, (const float*)E, P, x, d, vocab);
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

@@ -156,7 +156,8 @@ __global__ void fill_neg_inf(float* p, int n) {
 }
 
 __global__ void __launch_bounds__(NTHREADS)
-logmel_stft_kernel(const float* __restrict__ audio, const int* __restrict__ lens, int n_samples, int n_frames,
+logmel_stft_kernel(const float* __restrict__ audio, const long long* __restrict__ starts,
+                   const int* __restrict__ lens, int n_samples, int n_frames,
                    int n_mels, const LogmelTables* __restrict__ tables, const MelBankDev* __restrict__ bank,
                    float* __restrict__ out, float* __restrict__ clip_max) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -176,7 +177,9 @@ logmel_stft_kernel(const float* __restrict__ audio, const int* __restrict__ lens
   const int t0 = blockIdx.x * FT;
   const int tid = threadIdx.x;
   const int len = lens ? min(lens[b], n_samples) : n_samples;
-  const float* clip = audio + (size_t)b * n_samples;
+  // clip b = its own row of a [B, n_samples] matrix, or (window mode) n_samples starting at starts[b] inside one long
+  // recording: samples >= len read as zero, so a 15 s window is framed in place and its pad to 30 s is synthesised here
+  const float* clip = starts ? audio + starts[b] : audio + (size_t)b * n_samples;
 
 #ifdef KW_LOGMEL_TIMING
   long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dbg_t = clock64();
@@ -385,8 +388,8 @@ static int get_tables(int n_mels, const LogmelTables** tables, const MelBankDev*
 
 extern std::atomic<long long> g_launches;
 
-int logmel_launch(const float* audio, const int32_t* lens, int B, int n_samples, int n_mels, float* out,
-                  float* clip_max, cudaStream_t st) {
+int logmel_launch(const float* audio, const long long* starts, const int32_t* lens, int B, int n_samples, int n_mels,
+                  float* out, float* clip_max, cudaStream_t st) {
   KW_REQUIRE(B > 0 && n_mels > 0 && n_mels <= MAX_MELS, "kw_logmel: bad B=%d n_mels=%d", B, n_mels);
   KW_REQUIRE(n_samples >= NFFT, "kw_logmel: n_samples=%d must be >= 400", n_samples);
   const LogmelTables* tables;
@@ -407,7 +410,8 @@ int logmel_launch(const float* audio, const int32_t* lens, int B, int n_samples,
     const int nb = std::min(SLAB, B - b0);
     fill_neg_inf<<<ceil_div(nb, 128), 128, 0, st>>>(clip_max + b0, nb);
     dim3 grid(ceil_div(n_frames, FT), nb);
-    logmel_stft_kernel<<<grid, NTHREADS, smem, st>>>(audio + (size_t)b0 * n_samples, lens ? lens + b0 : nullptr,
+    logmel_stft_kernel<<<grid, NTHREADS, smem, st>>>(starts ? audio : audio + (size_t)b0 * n_samples,
+                                                     starts ? starts + b0 : nullptr, lens ? lens + b0 : nullptr,
                                                      n_samples, n_frames, n_mels, tables, bank,
                                                      out + (size_t)b0 * n_mels * n_frames, clip_max + b0);
     KW_LAUNCH_OK();

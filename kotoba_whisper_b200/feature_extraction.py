@@ -74,6 +74,10 @@ class WhisperFeatureExtractorB200:
             raise ValueError("the CUDA log-mel kernel implements Whisper's fixed n_fft=400 / hop_length=160 framing")
         if not 0 < feature_size <= 128 or feature_size % 4:
             raise ValueError(f"feature_size={feature_size} unsupported (multiple of 4, <= 128)")
+        if dither != 0.0:
+            # HF adds the noise per FRAME inside the spectrogram (audio_utils.py:764-765), i.e. overlapping frames see
+            # independent noise; a waveform-level dither would have different statistics.  The reference never sets it.
+            raise NotImplementedError("dither != 0 is not implemented by the CUDA log-mel kernel (reference default is 0)")
         self.feature_size = feature_size
         self.sampling_rate = sampling_rate
         self.hop_length = hop_length
@@ -109,6 +113,37 @@ class WhisperFeatureExtractorB200:
             st = torch.cuda.current_stream(audio.device).cuda_stream
             _lib.check(lib.kw_logmel(audio.data_ptr(), lens_ptr, B, n, self.feature_size, out.data_ptr(),
                                      clip_max.data_ptr(), st), "kw_logmel")
+        return out
+
+    def logmel_windows(self, recording: torch.Tensor, starts: torch.Tensor, lens: torch.Tensor,
+                       n_samples: Optional[int] = None) -> torch.Tensor:
+        """Device-side chunker (HF pipelines/automatic_speech_recognition.py:61-84): `recording` is ONE CUDA f32 waveform
+        [n_total] uploaded once; window w = samples [starts[w], starts[w] + lens[w]) is featurised in place as if it had
+        been sliced out and right-padded with zeros to `n_samples` (default 30 s) -> CUDA f32 [W, n_mels, n_samples//160].
+        No per-window host slicing, staging or re-upload of the (mostly zero) padded windows."""
+        if not recording.is_cuda:
+            raise _lib.KwError("logmel_windows needs a CUDA tensor (there is no CPU path)")
+        n = int(n_samples or self.n_samples)
+        recording = recording.contiguous().to(torch.float32).reshape(-1)
+        starts = torch.as_tensor(starts, dtype=torch.int64)
+        lens = torch.as_tensor(lens, dtype=torch.int32)
+        if starts.numel() != lens.numel() or starts.numel() == 0:
+            raise ValueError("starts / lens must be non-empty and of equal length")
+        if int(lens.max()) > n or int(lens.min()) < 1 or int(starts.min()) < 0 or \
+                int((starts + lens.to(torch.int64)).max()) > recording.numel():
+            raise ValueError("window outside the recording or longer than n_samples")
+        W = starts.numel()
+        dev = recording.device
+        starts_d, lens_d = starts.to(dev), lens.to(dev)
+        out = torch.empty((W, self.feature_size, n // self.hop_length), dtype=torch.float32, device=dev)
+        clip_max = torch.empty((W,), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.kw_logmel_windows(recording.data_ptr(), starts_d.data_ptr(), lens_d.data_ptr(), W, n,
+                                             self.feature_size, out.data_ptr(), clip_max.data_ptr(), st),
+                       "kw_logmel_windows")
+        out._kw_keep = (recording, starts_d, lens_d)  # alive until the stream has consumed them
         return out
 
     # ---- host staging: clips -> pinned buffer -> device, chunk by chunk ------------------------------------------------
@@ -197,9 +232,11 @@ class WhisperFeatureExtractorB200:
         if padding in ("max_length", True) or padding is None and max_length is not None:
             target = max_length if max_length else self.n_samples
         elif padding == "longest":
+            # HF always hands `max_length or n_samples` to pad(), and truncation applies whatever the padding strategy
+            # is (feature_extraction_whisper.py:296-303): clips longer than that are cut before "longest" is taken
             target = max(lens)
-            if max_length is not None and truncation:
-                target = min(target, max_length)
+            if truncation:
+                target = min(target, max_length if max_length else self.n_samples)
         elif padding in (False, "do_not_pad", None):
             if len(set(lens)) != 1:
                 raise ValueError("padding disabled but clips have different lengths")
@@ -224,8 +261,6 @@ class WhisperFeatureExtractorB200:
             mean = (audio * mask).sum(1, keepdim=True) / cnt
             var = (((audio - mean) * mask) ** 2).sum(1, keepdim=True) / cnt
             audio = torch.where(mask, (audio - mean) / torch.sqrt(var + 1e-7), torch.full_like(audio, self.padding_value))
-        if self.dither != 0.0:
-            audio = audio + self.dither * torch.randn_like(audio)
         feats = self.logmel_device(audio)
 
         out = BatchFeature()
@@ -253,3 +288,102 @@ class WhisperFeatureExtractorB200:
         if any(f.shape[-1] != T for f in feats):
             feats = [np.pad(f, ((0, 0), (0, T - f.shape[-1])), constant_values=self.padding_value) for f in feats]
         return BatchFeature({"input_features": _convert(np.stack(feats, 0), return_tensors)})
+
+
+class LogMelProducer:
+    """Dataset-scale log-mel producer: the `dataset.map(log_mel_transformation, batched=True)` stage of
+    run_data_filtering.py:335-356 / run_data_filtering_v3.py:260-275 (whole corpus -> `.vectorized` features) as a
+    streaming slab loop.  Slab i's host staging + H2D copy, slab i-1's kernel and slab i-2's D2H copy run concurrently
+    on three streams over double-buffered pinned / device slabs; the consumer receives host float32 arrays
+    [n, n_mels, 3000] (views into pinned memory, valid until the next item is requested).
+
+        prod = LogMelProducer(fe, slab_clips=256)
+        for first_index, feats in prod.produce(batches):      # batches: iterable of lists of 1-D float arrays
+            writer.write(feats)                                # e.g. the Arrow writer of datasets.map
+    """
+
+    def __init__(self, feature_extractor: "WhisperFeatureExtractorB200", slab_clips: int = 256):
+        self.fe = feature_extractor
+        self.slab = int(slab_clips)
+        self.dev = feature_extractor.device if feature_extractor.device.index is not None else \
+            torch.device("cuda", torch.cuda.current_device())
+        n, nm = feature_extractor.n_samples, feature_extractor.feature_size
+        nf = n // feature_extractor.hop_length
+        self._in_host = [torch.empty((self.slab, n), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._out_host = [torch.empty((self.slab, nm, nf), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._in_dev = [torch.empty((self.slab, n), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self._out_dev = [torch.empty((self.slab, nm, nf), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self._lens_host = [torch.empty((self.slab,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._lens_dev = [torch.empty((self.slab,), dtype=torch.int32, device=self.dev) for _ in range(2)]
+        self._cmax = [torch.empty((self.slab,), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self._s_in, self._s_run, self._s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self._ev_in = [torch.cuda.Event() for _ in range(2)]
+        self._ev_run = [torch.cuda.Event() for _ in range(2)]
+        self._ev_out = [torch.cuda.Event() for _ in range(2)]
+        self._used = [False, False]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _submit(self, slot: int, clips) -> int:
+        fe, n = self.fe, self.fe.n_samples
+        nb = len(clips)
+        if nb > self.slab:
+            raise ValueError(f"batch of {nb} clips exceeds slab_clips={self.slab}")
+        if self._used[slot]:
+            self._ev_out[slot].synchronize()  # slot's previous results were copied out (and handed to the consumer)
+        host = self._in_host[slot].numpy()
+        lens = self._lens_host[slot].numpy()
+
+        def stage(i):
+            c = np.asarray(clips[i], dtype=np.float32).reshape(-1)
+            k = min(len(c), n)
+            host[i, :k] = c[:k]
+            lens[i] = k  # the kernel reads samples >= len as zero: the pad is never staged or copied as zeros
+
+        if nb >= 16:
+            list(_staging_pool().map(stage, range(nb)))
+        else:
+            for i in range(nb):
+                stage(i)
+        with torch.cuda.stream(self._s_in):
+            if self._used[slot]:
+                self._s_in.wait_event(self._ev_run[slot])  # the kernel of slab i-2 has read in_dev[slot]
+            self._in_dev[slot][:nb].copy_(self._in_host[slot][:nb], non_blocking=True)
+            self._lens_dev[slot][:nb].copy_(self._lens_host[slot][:nb], non_blocking=True)
+            self._ev_in[slot].record(self._s_in)
+        lib = _lib.load()
+        with torch.cuda.device(self.dev):
+            self._s_run.wait_event(self._ev_in[slot])
+            if self._used[slot]:
+                self._s_run.wait_event(self._ev_out[slot])  # out_dev[slot] was copied out
+            _lib.check(lib.kw_logmel(self._in_dev[slot].data_ptr(), self._lens_dev[slot].data_ptr(), nb, n,
+                                     fe.feature_size, self._out_dev[slot].data_ptr(), self._cmax[slot].data_ptr(),
+                                     self._s_run.cuda_stream), "kw_logmel")
+            self._ev_run[slot].record(self._s_run)
+        with torch.cuda.stream(self._s_out):
+            self._s_out.wait_event(self._ev_run[slot])
+            self._out_host[slot][:nb].copy_(self._out_dev[slot][:nb], non_blocking=True)
+            self._ev_out[slot].record(self._s_out)
+        self._used[slot] = True
+        self.h2d_bytes += nb * n * 4
+        self.d2h_bytes += self._out_host[slot][:nb].numel() * 4
+        return nb
+
+    def produce(self, batches):
+        """batches: iterable of sequences of clips (each <= slab_clips long) -> yields (index of first clip, features)."""
+        pending = None  # (slot, nb, first index)
+        index, i = 0, 0
+        for clips in batches:
+            slot = i % 2
+            nb = self._submit(slot, clips)
+            if pending is not None:
+                ps, pn, pi = pending
+                self._ev_out[ps].synchronize()
+                yield pi, self._out_host[ps][:pn].numpy()
+            pending = (slot, nb, index)
+            index += nb
+            i += 1
+        if pending is not None:
+            ps, pn, pi = pending
+            self._ev_out[ps].synchronize()
+            yield pi, self._out_host[ps][:pn].numpy()

@@ -108,6 +108,17 @@ class EncoderOutput:
         return (self.last_hidden_state,)[i]
 
 
+@dataclass
+class Seq2SeqOutput:
+    """The Seq2SeqLMOutput fields the distillation step reads (run_distillation.py:641-652)."""
+    loss: Optional[torch.Tensor]
+    logits: torch.Tensor
+    encoder_last_hidden_state: Optional[torch.Tensor] = None
+
+    def __getitem__(self, k):
+        return getattr(self, k) if isinstance(k, str) else tuple(v for v in (self.loss, self.logits) if v is not None)[k]
+
+
 def _dev_tensor(t: torch.Tensor, dtype: torch.dtype, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=dtype).contiguous()
 
@@ -274,9 +285,9 @@ class WhisperB200ForConditionalGeneration:
         B = input_features.shape[0]
         if B > self.max_batch:
             raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
+        # bf16 models: the reference casts features to the model dtype (run_pseudo_labelling.py:338); here the rounding
+        # happens where the conv1 im2col kernel stores its bf16 operand — no separate cast kernels
         mel = input_features.to(device=self.device, dtype=torch.float32).contiguous()
-        if self.dtype == torch.bfloat16:  # the reference casts features to the model dtype (run_pseudo_labelling.py:338)
-            mel = mel.to(torch.bfloat16).to(torch.float32)
         out = torch.empty((B, c.max_source_positions, c.d_model), dtype=torch.float32, device=self.device) \
             if return_hidden else None
         with torch.cuda.device(self.device):
@@ -368,7 +379,7 @@ class WhisperB200ForConditionalGeneration:
                           ("logprob_threshold", logprob_threshold), ("no_speech_threshold", no_speech_threshold),
                           ("return_token_timestamps", return_token_timestamps),
                           ("return_dict_in_generate", return_dict_in_generate)):
-            if val:
+            if val is not None and val is not False and not (isinstance(val, (list, tuple)) and len(val) == 0):
                 raise NotImplementedError(f"`{name}` is outside the greedy transcription path this library implements")
         if temperature not in (None, 0, 0.0) and temperature != (0.0,):
             raise NotImplementedError("sampling / temperature fallback is outside the greedy transcription path")
@@ -378,6 +389,19 @@ class WhisperB200ForConditionalGeneration:
             raise NotImplementedError("sampling is outside the greedy transcription path")
         g = WhisperB200GenerationConfig.from_any(generation_config) if generation_config is not None \
             else self.generation_config
+        if g is not self.generation_config:
+            # the device-side token rules (eos / pad / suppress lists / timestamp ids) were uploaded at construction
+            # from self.generation_config; a per-call config may only differ in host-side fields
+            baked = ("eos_token_id", "pad_token_id", "no_timestamps_token_id", "max_initial_timestamp_index")
+            for k in baked:
+                if getattr(g, k) != getattr(self.generation_config, k):
+                    raise ValueError(f"per-call generation_config.{k}={getattr(g, k)!r} differs from the value baked "
+                                     f"into the device token rules ({getattr(self.generation_config, k)!r}); build "
+                                     "the model with that generation_config instead")
+            for k in ("suppress_tokens", "begin_suppress_tokens"):
+                if list(getattr(g, k) or []) != list(getattr(self.generation_config, k) or []):
+                    raise ValueError(f"per-call generation_config.{k} differs from the list baked into the device "
+                                     "token rules; build the model with that generation_config instead")
         c = self.config
         encoder_outputs = kwargs.pop("encoder_outputs", None)
         max_length = kwargs.pop("max_length", None)
@@ -467,8 +491,8 @@ class WhisperB200ForConditionalGeneration:
                     seek[b] += adv
                     for s in segs:
                         out[b].extend(s)
-            if encoder_outputs is not None:
-                break
+            # encoder_outputs: HF keeps the seek loop running over the SAME encoder output (input_features is None, so
+            # _get_input_segment has nothing to re-slice; generation_whisper.py:785-903) — so does this loop.
         if stats is not None:
             stats["passes"] = n_pass
         L = max((len(o) for o in out), default=0)
@@ -480,6 +504,61 @@ class WhisperB200ForConditionalGeneration:
         if return_segments:
             return {"sequences": res, "segments": out}
         return res
+
+    # ---- teacher-forcing forward (distillation's frozen teacher) -----------------------------------------------------
+    @torch.no_grad()
+    def forward(self, input_features: Optional[torch.Tensor] = None, attention_mask=None,
+                decoder_input_ids: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                encoder_outputs=None, **kwargs) -> "Seq2SeqOutput":
+        """`teacher_model(encoder_outputs=..., labels=...)` / `teacher_model(**batch)` of run_distillation.py:641-649
+        (WhisperForConditionalGeneration.forward, HF/models/whisper/modeling_whisper.py:964-1100): all target positions
+        at once, no cache -> fp32 logits [B, T, vocab] on the device (+ the cross-entropy `loss` when labels are given).
+        `labels` are shifted right into decoder inputs exactly as HF does (:68-81, -100 -> pad_token_id)."""
+        drop = {k: kwargs.pop(k) for k in ("use_cache", "return_dict", "output_attentions", "output_hidden_states",
+                                           "decoder_attention_mask", "past_key_values", "cache_position") if k in kwargs}
+        if drop.get("decoder_attention_mask") is not None or drop.get("past_key_values") is not None:
+            raise NotImplementedError("decoder_attention_mask / past_key_values are outside the teacher-forcing path")
+        if kwargs:
+            raise TypeError(f"forward() got unsupported keyword arguments: {sorted(kwargs)}")
+        c = self.config
+        if labels is not None:
+            if labels.shape[1] > c.max_target_positions:
+                raise ValueError(f"Labels' sequence length {labels.shape[1]} cannot exceed the maximum allowed length "
+                                 f"of {c.max_target_positions} tokens.")
+            if decoder_input_ids is None:
+                decoder_input_ids = labels.new_zeros(labels.shape)
+                decoder_input_ids[:, 1:] = labels[:, :-1]
+                decoder_input_ids[:, 0] = c.decoder_start_token_id
+                decoder_input_ids = decoder_input_ids.masked_fill(decoder_input_ids == -100, c.pad_token_id)
+        if decoder_input_ids is None:
+            raise ValueError("forward() needs `decoder_input_ids` or `labels`")
+        B, T = decoder_input_ids.shape
+        if B > self.max_batch:
+            raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
+        if encoder_outputs is not None:
+            enc = encoder_outputs[0] if not isinstance(encoder_outputs, torch.Tensor) else encoder_outputs
+            e = enc.to(device=self.device, dtype=torch.float32).contiguous()
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.kw_set_encoder_output(self._handle, e.data_ptr(), B, self._stream()),
+                           "kw_set_encoder_output")
+            self._last_mel = e
+            enc_hidden = enc
+        else:
+            if input_features is None:
+                raise ValueError("forward() needs `input_features` or `encoder_outputs`")
+            enc_hidden = self.encode(input_features, return_hidden=True)
+        ids = decoder_input_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        logits = torch.empty((B, T, c.vocab_size), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.kw_decoder_forward(self._handle, ids.data_ptr(), B, T, logits.data_ptr(),
+                                                    self._stream()), "kw_decoder_forward")
+        loss = None
+        if labels is not None:  # CrossEntropyLoss over all positions, ignore_index = -100 (:1086-1090)
+            loss = torch.nn.functional.cross_entropy(logits.view(-1, c.vocab_size),
+                                                     labels.to(self.device).reshape(-1), ignore_index=-100)
+        return Seq2SeqOutput(loss=loss, logits=logits, encoder_last_hidden_state=enc_hidden)
+
+    __call__ = forward
 
     # ---- test hooks ------------------------------------------------------------------------------------------------------
     def step_logits(self, tokens: torch.Tensor, pos: int) -> torch.Tensor:

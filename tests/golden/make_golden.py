@@ -1,7 +1,7 @@
 """Generate the golden fixtures under tests/golden/ by running the REFERENCE implementation
 (transformers' Whisper — the code the reference repo calls at run_pseudo_labelling.py:268,338) on CPU fp32.
 
-    python tests/golden/make_golden.py [logmel] [tiny] [kotoba] [teacher]
+    python tests/golden/make_golden.py [logmel] [tiny] [tiny_extra] [kotoba] [teacher] [teacher_tf]
 
 Inputs are seeded synthetic audio (tests/_synth.py) and random-init weights (torch.manual_seed(0), tests/_hf.py), so
 every consumer can rebuild bit-identical inputs; only the (small) outputs are committed.  Run in the build container;
@@ -78,6 +78,83 @@ def golden_tiny():
     print("tiny.npz written")
 
 
+def longform_batch(n_mels=128):
+    """3 recordings of 70 / 45 / 33 s, zero-padded to the longest, featurised as one batch + frame attention mask
+    (what WhisperFeatureExtractor(..., padding="longest", return_attention_mask=True, truncation=False) produces)."""
+    from oracle.logmel_ref import logmel_f64
+    rng = np.random.default_rng(21)
+    secs = [70, 45, 33]
+    n_max = 16000 * max(secs)
+    audio = [(rng.standard_normal(16000 * s) * 0.1).astype(np.float32) for s in secs]
+    mel = np.stack([logmel_f64(np.pad(a, (0, n_max - len(a))), n_mels, n_samples=n_max) for a in audio])
+    mask = np.zeros((3, n_max // 160), np.int64)
+    for i, s in enumerate(secs):
+        mask[i, : 16000 * s // 160] = 1
+    return torch.from_numpy(mel), torch.from_numpy(mask)
+
+
+def golden_tiny_extra():
+    """generate(encoder_outputs=...) with timestamps on / off (HF keeps its seek loop running on the same encoder
+    output), batched long-form with attention_mask (batch shrinking), and teacher-forcing logits (labels=...)."""
+    from transformers.modeling_outputs import BaseModelOutput
+    out = {}
+    model = build_hf(TINY)
+    mel = torch.from_numpy(logmel_batch_f64(clips("UGS", 7), 128))
+    with torch.no_grad():
+        enc = model.model.encoder(mel).last_hidden_state
+        ids = model.generate(encoder_outputs=BaseModelOutput(last_hidden_state=enc), language="ja",
+                             task="transcribe", return_timestamps=False, max_length=40, num_beams=1)
+        out["encout_ids_ts0"] = ids.numpy().astype(np.int64)
+        # with timestamps HF keeps seeking over the SAME encoder output (generation_whisper.py:785-903 with
+        # input_features=None); for B > 1 its batch shrinking crashes on the missing input_features (:1823) as soon as
+        # one row finishes early, so the defined behaviour is per row
+        for b in range(3):
+            ids = model.generate(encoder_outputs=BaseModelOutput(last_hidden_state=enc[b:b + 1]), language="ja",
+                                 task="transcribe", return_timestamps=True, max_length=40, num_beams=1)
+            out[f"encout_ids_ts1_row{b}"] = ids.numpy().astype(np.int64)
+            print("encoder_outputs ts row", b, tuple(ids.shape))
+        lmel, lmask = longform_batch()
+        ids = model.generate(lmel, attention_mask=lmask, language="ja", task="transcribe", return_timestamps=True,
+                             max_length=64, num_beams=1)
+        out["longform_b3_ids"] = ids.numpy().astype(np.int64)
+        print("long-form B=3", tuple(ids.shape))
+        # teacher forcing: labels [3, 24] with -100 padding on the last rows
+        g = torch.Generator().manual_seed(5)
+        labels = torch.randint(0, 50257, (3, 24), generator=g)
+        labels[1, 18:] = -100
+        labels[2, 9:] = -100
+        res = model(input_features=mel, labels=labels)
+        out["tf_labels"] = labels.numpy().astype(np.int64)
+        out["tf_logits_sub"] = res.logits[:, :, ::53].numpy().astype(np.float32)
+        out["tf_loss"] = np.array(float(res.loss))
+        res2 = model(encoder_outputs=BaseModelOutput(last_hidden_state=enc), decoder_input_ids=labels.clamp(min=0))
+        out["tf_logits_ids_sub"] = res2.logits[:, :, ::53].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "tiny_extra.npz"), **out)
+    print("tiny_extra.npz written")
+
+
+def golden_teacher_tf():
+    """Teacher-forcing logits at T = 128 (max_label_length of the reference's distillation configs) for the kotoba and
+    teacher architectures: model(input_features, labels) as run_distillation.py:641-649 calls the frozen teacher."""
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    labels = torch.randint(0, 50257, (2, 128), generator=g)
+    labels[1, 90:] = -100
+    out["labels"] = labels.numpy().astype(np.int64)
+    mel = torch.from_numpy(logmel_batch_f64(clips("GS", 3000), 128))
+    for name, arch in (("kotoba", KOTOBA), ("teacher", TEACHER)):
+        t0 = time.time()
+        model = build_hf(arch)
+        with torch.no_grad():
+            res = model(input_features=mel, labels=labels)
+        out[f"{name}_logits_sub"] = res.logits[:, :, ::212].numpy().astype(np.float32)
+        out[f"{name}_loss"] = np.array(float(res.loss))
+        print(name, "teacher-forcing", tuple(res.logits.shape), f"{time.time() - t0:.1f}s", flush=True)
+        del model
+    np.savez_compressed(os.path.join(HERE, "teacher_tf.npz"), **out)
+    print("teacher_tf.npz written")
+
+
 def golden_full(name, arch, spec, seed0, cases):
     out = {}
     t0 = time.time()
@@ -96,6 +173,10 @@ if __name__ == "__main__":
         golden_logmel()
     if "tiny" in what:
         golden_tiny()
+    if "tiny_extra" in what:
+        golden_tiny_extra()
+    if "teacher_tf" in what:
+        golden_teacher_tf()
     if "kotoba" in what:  # BASELINE.json configs[0]: batch 4 x 30 s, ja/transcribe, timestamps, max_length 128
         golden_full("kotoba", KOTOBA, "UGSG", 1000, [(True, 128, "ja", "transcribe"), (False, 128, "ja", "transcribe")])
     if "teacher" in what:  # configs[2] architecture at a CPU-runnable batch of 2

@@ -18,7 +18,7 @@ def _free_port():
 def _worker(rank, world, port, n_items, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from kotoba_whisper_b200.distributed import gather_token_ids, shard_range
+    from kotoba_whisper_b200.distributed import TokenGather, gather_token_ids, shard_range
     a, b = shard_range(n_items, rank, world)
     # "transcribe" item i -> i+1 tokens of value 100+i (ragged lengths, like per-rank generate outputs)
     L = max((i + 1 for i in range(a, b)), default=0)
@@ -27,8 +27,13 @@ def _worker(rank, world, port, n_items, q):
         ids[r, : i + 1] = 100 + i
     out = gather_token_ids(ids, 50257)
     fixed = gather_token_ids(ids, 50257, max_len=n_items + 3)
+    # fixed-shape single-collective form, two batches in flight before the first is read (the bench's pipelining)
+    tg = TokenGather(rows_per_rank=4, max_len=n_items + 1, pad_token_id=50257)
+    h1 = tg.submit(ids.to(torch.int32))
+    h2 = tg.submit((ids + 1).to(torch.int32))
+    g1, g2 = h1.result().clone(), h2.result().clone()
     if rank == 0:
-        q.put((out, fixed))
+        q.put((out, fixed, g1, g2))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -41,7 +46,7 @@ def test_shard_and_gather_world2():
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_items, q)) for r in range(world)]
     for p in procs:
         p.start()
-    out, fixed = q.get(timeout=120)
+    out, fixed, g1, g2 = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -49,3 +54,12 @@ def test_shard_and_gather_world2():
     for i in range(n_items):
         assert (out[i, : i + 1] == 100 + i).all() and (out[i, i + 1:] == 50257).all()
         assert (fixed[i, : i + 1] == 100 + i).all() and (fixed[i, i + 1:] == 50257).all()
+    # TokenGather: rank r's rows sit at [4r, 4r + rows_r), padded to 4 rows x (n_items + 1) columns
+    assert g1.shape == (8, n_items + 1) and g1.dtype == torch.int32
+    from kotoba_whisper_b200.distributed import shard_range
+    for r in range(world):
+        a, b = shard_range(n_items, r, world)
+        for k, i in enumerate(range(a, b)):
+            assert (g1[4 * r + k, : i + 1] == 100 + i).all() and (g1[4 * r + k, i + 1:] == 50257).all()
+            assert (g2[4 * r + k, : i + 1] == 101 + i).all()
+        assert (g1[4 * r + (b - a): 4 * (r + 1)] == 50257).all()

@@ -96,20 +96,30 @@ def _first_divergence(a, b):
 
 
 def test_tiny_bf16_vs_rounded_weight_oracle():
-    model, ref = build_pair(TINY, torch.bfloat16, max_batch=4, oracle_weights="rounded")
-    mel = torch.from_numpy(logmel_batch_f64(clips("UGS", 7), 128))
+    """bf16 bar on the tiny architecture: encoder cosine >= 0.999 vs the fp32 oracle on bf16-rounded weights; the
+    product's fp32 path on those weights is token-identical to the oracle; the bf16 path agrees with it on every
+    utterance up to near-ties (divergences whose fp32 logit gap is below 4 sigma of the bf16 logit noise)."""
+    from kotoba_whisper_b200 import WhisperB200ForConditionalGeneration
+    from kotoba_whisper_b200.parity import bf16_token_parity, rounded_state_dict
+    from _gpu_util import state_dict_for
+    model, ref = build_pair(TINY, torch.bfloat16, max_batch=12, oracle_weights="rounded")
+    sd, cfg = state_dict_for(tuple(sorted(TINY.items())))
+    m32 = WhisperB200ForConditionalGeneration.from_state_dict(rounded_state_dict(sd), cfg, dtype=torch.float32,
+                                                              max_batch=12, device="cuda:0")
+    mel = torch.from_numpy(logmel_batch_f64(clips("UGSUGSUGSUGS", 7), 128))
     mel_r = mel.to(torch.bfloat16).to(torch.float32)
     enc = model.encode(mel.cuda()).cpu()
     with torch.no_grad():
         enc_ref = ref.encode(mel_r)
     cos = torch.nn.functional.cosine_similarity(enc.flatten(1), enc_ref.flatten(1), dim=1)
     assert cos.min() >= 0.999, cos
-    ids = model.generate(mel.cuda(), language="ja", task="transcribe", return_timestamps=False, max_length=64).cpu()
+    ids32 = m32.generate(mel_r.cuda(), language="ja", task="transcribe", return_timestamps=False, max_length=64).cpu()
     with torch.no_grad():
         want = ref.generate(mel_r, language="ja", task="transcribe", return_timestamps=False, max_length=64)
-    same = sum(int(ids.shape == want.shape and torch.equal(ids[i], want[i])) for i in range(ids.shape[0]))
-    print(f"bf16 tiny: {same}/{ids.shape[0]} utterances token-identical to the fp32 oracle on rounded weights")
-    assert ids.shape[0] == 3
+    assert torch.equal(ids32, want), "fp32 path on rounded weights must be token-identical to the oracle"
+    res = bf16_token_parity(model, m32, mel, max_length=64)
+    assert res["adjusted_identical"] == res["utterances"], res
+    assert res["raw_identical"] >= 1, res
 
 
 def _check_fullsize(golden, name, arch, spec, seed, cases, max_batch):
@@ -172,35 +182,69 @@ def test_bf16_tensor_path_matches_simt_path(arch):
     cos = torch.nn.functional.cosine_similarity(enc_t.flatten(1), enc_s.flatten(1), dim=1)
     assert cos.min() >= 0.9995
     assert _rel(lg_t, lg_s) <= 3e-2
-    print("bf16 tc vs simt greedy tokens identical:", torch.equal(ids_t, ids_s))
+    # greedy tokens: identical, or first divergence at a near-tie of the SIMT path's own logits (gap < 4 sigma of the
+    # tensor-vs-SIMT logit difference)
+    sigma = (lg_t - lg_s).double().pow(2).mean().sqrt().item()
+    lib.kw_set_gemm_impl(1)
+    try:
+        model.encode(mel)
+        model.cross_kv(3)
+        for b in range(3):
+            a, c = ids_t[b].tolist(), ids_s[b].tolist()
+            n = min(len(a), len(c))
+            j = next((i for i in range(n) if a[i] != c[i]), -1)
+            if j < 0:
+                continue
+            hist = torch.tensor([[50258, 50266, 50360] + c[:j]] * 3, dtype=torch.int32, device="cuda")
+            for pos in range(hist.shape[1]):
+                lg = model.step_logits(hist, pos)
+            gap = float(lg[b, c[j]] - lg[b, a[j]])
+            assert abs(gap) < 4 * sigma, (b, j, gap, sigma)
+    finally:
+        lib.kw_set_gemm_impl(0)
 
 
-def test_kotoba_bf16_vs_fp32_exact_path_on_rounded_weights():
-    """BASELINE north_star bf16 bar at full size: encoder cosine >= 0.999 and token agreement, measured against the
-    exact-fp32 CUDA path (itself bit-identical to HF, see test_kotoba_fp32_tokens_bit_identical) run on the SAME
-    bf16-rounded weights and bf16-rounded features, so only arithmetic precision differs.  Token agreement is reported,
-    not asserted at 99 %: with random-init weights the top-2 logit margin is ~1e-2, so a single bf16-level
-    perturbation flips a greedy step and the sequences diverge from there."""
-    from kotoba_whisper_b200 import WhisperB200ForConditionalGeneration
+def test_kotoba_bf16_token_parity_bar():
+    """BASELINE north_star bf16 bar on the benchmarked configuration (kotoba-v2.0 architecture, greedy short-form,
+    max_length 128), 128 utterances: encoder cosine >= 0.999 and token sequences identical on >= 99 % of utterances
+    against the exact-fp32 CUDA path (itself bit-identical to HF, test_kotoba_fp32_tokens_bit_identical) on the SAME
+    bf16-rounded weights and features.  With random-init weights the top-2 logit gap is of the order of the bf16 logit
+    noise, so identity is counted up to near-ties (kotoba_whisper_b200/parity.py: a first divergence whose fp32 logit gap
+    is below tau = 4 sigma of the measured bf16 logit noise is a tie); the raw figure must not be worse than what HF's
+    own bf16 (sdpa, same GPU, same weights) achieves against the same fp32 tokens, within 10 points of sampling noise.
+    tools/bf16_parity.py writes the same measurement to profiles/r2_bf16_parity.json."""
+    from kotoba_whisper_b200 import WhisperB200ForConditionalGeneration, WhisperFeatureExtractorB200
+    from kotoba_whisper_b200.parity import bf16_token_parity, rounded_state_dict, first_divergence, _trim
     from _gpu_util import state_dict_for
+    from _hf import build_hf
+    from _synth import clip
+    N = 128
     sd, cfg = state_dict_for(tuple(sorted(KOTOBA.items())))
-    rounded = {k: (v.to(torch.bfloat16).to(torch.float32) if v.dim() >= 2 and "embed_positions" not in k else v)
-               for k, v in sd.items()}
-    m16 = WhisperB200ForConditionalGeneration.from_state_dict(rounded, cfg, dtype=torch.bfloat16, max_batch=8, device="cuda:0")
-    m32 = WhisperB200ForConditionalGeneration.from_state_dict(rounded, cfg, dtype=torch.float32, max_batch=8, device="cuda:0")
-    mel = torch.from_numpy(logmel_batch_f64(clips("UGSGUGSG", 2000), 128)).cuda()
-    mel = mel.to(torch.bfloat16).to(torch.float32)
-    e16, e32 = m16.encode(mel), m32.encode(mel)
+    rounded = rounded_state_dict(sd)
+    m16 = WhisperB200ForConditionalGeneration.from_state_dict(rounded, cfg, dtype=torch.bfloat16, max_batch=32, device="cuda:0")
+    m32 = WhisperB200ForConditionalGeneration.from_state_dict(rounded, cfg, dtype=torch.float32, max_batch=32, device="cuda:0")
+    fe = WhisperFeatureExtractorB200(feature_size=128, device="cuda:0")
+    audio = [clip("UGSG"[i % 4], 7000 + i) for i in range(N)]
+    mel = torch.cat([fe(audio[i:i + 32], sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"]
+                     for i in range(0, N, 32)])
+    mel_r = mel.to(torch.bfloat16).to(torch.float32)
+    e16, e32 = m16.encode(mel_r[:8]), m32.encode(mel_r[:8])
     cos = torch.nn.functional.cosine_similarity(e16.flatten(1), e32.flatten(1), dim=1)
     assert cos.min().item() >= 0.999, cos
-    a = m16.generate(mel, language="ja", task="transcribe", return_timestamps=False, max_length=64).cpu()
-    b = m32.generate(mel, language="ja", task="transcribe", return_timestamps=False, max_length=64).cpu()
-    n = min(a.shape[1], b.shape[1])
-    prefix = []
-    for i in range(a.shape[0]):
-        d = (a[i, :n] != b[i, :n]).nonzero()
-        prefix.append(int(d[0]) if len(d) else n)
-    same = sum(int(p == n and a.shape == b.shape) for p in prefix)
-    print(f"bf16 vs fp32-exact (rounded weights): encoder cosine min {cos.min().item():.6f}; "
-          f"{same}/{a.shape[0]} utterances token-identical over {n} tokens; common prefix lengths {prefix}")
-    assert min(prefix) >= 1
+    res = bf16_token_parity(m16, m32, mel, max_length=128)
+    assert res["adjusted_pct"] >= 99.0, res
+    # HF's own bf16 against the same fp32 tokens
+    hf = build_hf(KOTOBA, seed=0)
+    hf.load_state_dict(rounded)
+    hf = hf.to(torch.bfloat16).cuda()
+    pad = m32.generation_config.pad_token_id
+    same_hf = 0
+    with torch.no_grad():
+        for i in range(0, N, 32):
+            x = mel_r[i:i + 32]
+            want = [_trim(r, pad) for r in m32.generate(x, language="ja", task="transcribe", return_timestamps=False,
+                                                        max_length=128).cpu().tolist()]
+            got = [_trim(r, pad) for r in hf.generate(x.to(torch.bfloat16), language="ja", task="transcribe",
+                                                      return_timestamps=False, max_length=128, num_beams=1).cpu().tolist()]
+            same_hf += sum(int(first_divergence(p, q) < 0) for p, q in zip(got, want))
+    assert res["raw_identical"] >= same_hf - int(0.10 * N), (res["raw_identical"], same_hf)
