@@ -57,9 +57,14 @@ def bf16_token_parity(m16, m32, mel: torch.Tensor, language="ja", task="transcri
         x = mel[c0:c0 + chunk].to(dev)
         x = x.to(torch.bfloat16).to(torch.float32)  # the bf16 model rounds its features; give both paths the same ones
         B = x.shape[0]
-        kw = dict(language=language, task=task, return_timestamps=return_timestamps, max_length=max_length)
-        a16 = [_trim(r, pad) for r in m16.generate(x, **kw).cpu().tolist()]
-        a32 = [_trim(r, pad) for r in m32.generate(x, **kw).cpu().tolist()]
+        # ONE decoder pass over the 30 s window on each path (kw_greedy_pass: prompt prefill + greedy loop), raw tokens:
+        # a first-divergence index then maps directly onto a decoder position.  (generate() may run further seek passes
+        # on sub-batches and splices segments, which would hide where two runs parted.)
+        def one_pass(m):
+            m.encode(x, return_hidden=False)
+            t = m._greedy_pass(B, prompt, max_length, bool(return_timestamps))[:, P:].tolist()
+            return [r[: r.index(eos)] if eos in r else _trim(r, pad) for r in t]
+        a16, a32 = one_pass(m16), one_pass(m32)
         div = [first_divergence(p, q) for p, q in zip(a16, a32)]
         first_div.extend(div)
         # teacher-force the fp32 path along its own tokens up to the last first-divergence position of the chunk
