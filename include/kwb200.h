@@ -231,6 +231,10 @@ void kw_debug_gemm_stamps(uint64_t* dev_buffer_16);
 void kw_set_gemm_impl(int32_t impl);
 /* 1: wide GEMMs (M >= 256) use the 2-CTA tcgen05 kernel (cta_group::2, 256 x 256 tiles per CTA pair); 0: 1-CTA kernel. */
 void kw_set_gemm_2cta(int32_t on);
+/* 1 (default): kw_greedy_pass of a bf16 model runs the whole position loop as ONE persistent kernel (LayerNorm + QKV,
+ * self-attention with KV append, cross-attention, fused GELU MLP, vocabulary projection with the logits processors and
+ * argmax in its epilogue); 0: one kernel per op (the exact-fp32 schedule; A/B reference).  Process-wide. */
+void kw_set_decode_impl(int32_t impl);
 /* counts kernels launched by this library since the last reset (bench.py's gpu_launches) */
 int64_t kw_launch_count(int32_t reset);
 

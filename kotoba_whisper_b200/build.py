@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkwb200.so")
-SOURCES = ["api.cu", "logmel.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_tc.cu", "attention.cu", "sampling.cu"]
+SOURCES = ["api.cu", "logmel.cu", "elementwise.cu", "gemm_simt.cu", "gemm_tc.cu", "attention_tc.cu", "attention.cu", "sampling.cu", "decode_fused.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("KW_NVCC_EXTRA", "").split()
 
@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 def _newer(src: str, dst: str) -> bool:
     if not os.path.exists(dst):
         return True
-    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(HERE, "..", "include", "kwb200.h")]
+    deps = [src, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"), os.path.join(CSRC, "model.cuh"), os.path.join(HERE, "..", "include", "kwb200.h")]
     return any(os.path.getmtime(d) > os.path.getmtime(dst) for d in deps if os.path.exists(d))
 
 

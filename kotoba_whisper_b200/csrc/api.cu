@@ -51,6 +51,15 @@ int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int
 int sample_launch(const float* logits, const unsigned char* flags, const SampleRules& r, int* tokens, int ld_tokens,
                   int B, int pos, int begin_index, int return_ts, int* finished, cudaStream_t st);
 
+// decode_fused.cu: the persistent decode kernel (bf16 models)
+int fused_decode_prepare(kw_model* m);
+int fused_decode_pass(kw_model* m, int B, int n_prompt, int max_length, int return_ts, int* tokens, cudaStream_t st);
+void fused_decode_destroy(kw_model* m);
+static std::atomic<int> g_decode_impl{[] {
+  const char* e = getenv("KW_DECODE_FUSED");
+  return e ? atoi(e) : 1;
+}()};
+
 int gemm(const GemmArgs& g, cudaStream_t st) {
   const int impl = g_gemm_impl.load();
   if (impl != 1 && g.a_type == KW_BF16 && g.w_type == KW_BF16) {
@@ -113,31 +122,7 @@ static double gemm_flops(const GemmArgs& g) { return 2.0 * g.M * (double)g.N * g
 
 using namespace kw;
 
-struct kw_model {
-  kw_config cfg;
-  kw_weights w;
-  std::vector<kw_enc_layer_weights> enc;
-  std::vector<kw_dec_layer_weights> dec;
-  SampleRules rules;
-  kw_dtype t;
-  // device pools
-  char* pool = nullptr;
-  size_t pool_bytes = 0;
-  unsigned char* flags = nullptr;  // [vocab] bit0 = suppress, bit1 = suppress at begin
-  // encoder workspaces
-  void *bufP = nullptr, *bufQ = nullptr, *a = nullptr, *o = nullptr, *enc_out = nullptr;
-  float* x = nullptr;
-  // decoder workspaces
-  float *dx = nullptr, *dqkv = nullptr, *dq = nullptr, *logits = nullptr;
-  void *da = nullptr, *dattn = nullptr, *dh = nullptr;  // projection operands: model dtype (bf16 feeds the tcgen05 path)
-  void* self_k = nullptr;  // [L][B][H][max_t][64]
-  void* self_v = nullptr;
-  void* xkv = nullptr;  // [L][B*S][2d]
-  int* finished = nullptr;
-  int* finished_host = nullptr;  // pinned
-  cudaEvent_t finished_copied = nullptr;
-  int enc_B = 0;
-};
+#include "model.cuh"
 
 extern "C" {
 
@@ -145,6 +130,7 @@ const char* kw_last_error(void) { return g_err; }
 const char* kw_version(void) { return "kwb200 0.1 (sm_100a)"; }
 void kw_set_gemm_impl(int32_t impl) { g_gemm_impl.store(impl); }
 void kw_set_gemm_2cta(int32_t on) { gemm_tc_set_2cta(on); }
+void kw_set_decode_impl(int32_t impl) { g_decode_impl.store(impl); }
 
 void kw_debug_attention_desc(int32_t v_lbo_bytes, int32_t v_sbo_bytes, int32_t v_kstep_bytes) {
   attention_tc_debug(v_lbo_bytes, v_sbo_bytes, v_kstep_bytes);
@@ -285,6 +271,7 @@ int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_ru
 
 void kw_model_destroy(kw_model* m) {
   if (!m) return;
+  fused_decode_destroy(m);
   cudaFree(m->pool);
   if (m->finished_host) cudaFreeHost(m->finished_host);
   if (m->finished_copied) cudaEventDestroy(m->finished_copied);
@@ -468,13 +455,25 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
   const double es_d = (double)esize(m->t), dd = m->cfg.d_model, Ld = m->cfg.dec_layers;
   const double w_layer_bytes = (6.0 * dd * dd + 2.0 * dd * m->cfg.ffn_dim) * es_d;
   double pass_bytes = 0.0;
+  auto position_bytes = [&](int pos) {
+    return Ld * w_layer_bytes + (pos >= n_prompt - 1 ? (double)m->cfg.vocab_size * dd * es_d : 0.0) +
+           Ld * B * 2.0 * m->cfg.max_source_pos * dd * es_d + Ld * B * 2.0 * (pos + 1) * dd * es_d;
+  };
   ProfScope pass_scope(KW_PROF_DEC_PASS, 0.0, st);
+  // bf16 models: the whole position loop is ONE persistent kernel (decode_fused.cu); the kernel-per-op schedule below is
+  // the exact-fp32 path and the A/B reference (kw_set_decode_impl(0) / KW_DECODE_FUSED=0)
+  if (m->t == KW_BF16 && g_decode_impl.load() != 0 && g_gemm_impl.load() != 1 && fused_decode_prepare(m) == KW_OK) {
+    const int done = fused_decode_pass(m, B, n_prompt, max_length, return_timestamps, tokens, st);
+    if (done < 0) return done;
+    for (int pos = 0; pos < done; ++pos) pass_bytes += position_bytes(pos);
+    if (g_prof.mask & (1u << KW_PROF_DEC_PASS)) g_prof.work[KW_PROF_DEC_PASS] += pass_bytes;
+    return done;
+  }
   for (int pos = 0; pos + 1 < max_length; ++pos) {
     const int sample = pos >= n_prompt - 1;
     KW_TRY(kw_decode_step(m, tokens, max_length, B, pos, n_prompt, sample, return_timestamps, m->finished, nullptr, stream));
     ++steps;
-    pass_bytes += Ld * w_layer_bytes + (sample ? (double)m->cfg.vocab_size * dd * es_d : 0.0) +
-                  Ld * B * 2.0 * m->cfg.max_source_pos * dd * es_d + Ld * B * 2.0 * (pos + 1) * dd * es_d;
+    pass_bytes += position_bytes(pos);
     const int generated = pos + 2 - n_prompt;  // tokens sampled so far
     if (check_every > 0 && sample && generated % check_every == 0 && pos + 2 < max_length && pending_since < 0) {
       KW_CUDA_OK(cudaMemcpyAsync(m->finished_host, m->finished, B * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -236,7 +236,7 @@ struct MapKey {
   const void* ptr;
   unsigned long long gdim[3], gstride[2];
   unsigned box[3];
-  int rank;
+  int rank, swizzle;
   bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
 };
 struct MapKeyHash {
@@ -251,13 +251,14 @@ struct MapKeyHash {
 // Encoded tensor maps are cached: workspaces and weights keep their addresses for the life of a model handle, so the
 // ~27 projections of every decode step hit the cache instead of calling into the driver.
 static inline int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* gdim,
-                                const cuuint64_t* gstride_bytes, const cuuint32_t* box) {
+                                const cuuint64_t* gstride_bytes, const cuuint32_t* box, bool swizzle128 = true) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr;
   key.rank = rank;
+  key.swizzle = swizzle128 ? 1 : 0;
   for (int i = 0; i < rank; ++i) { key.gdim[i] = gdim[i]; key.box[i] = box[i]; }
   for (int i = 0; i < rank - 1; ++i) key.gstride[i] = gstride_bytes[i];
   {
@@ -275,7 +276,8 @@ static inline int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, con
   }
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstride_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
