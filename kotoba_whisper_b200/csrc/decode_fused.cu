@@ -89,7 +89,12 @@ struct Params {
   unsigned* bar_counter;
   int* steps_out;
   int TR, n_kv_tiles;  // cross K/V tile rows, tiles per (batch, head)
+  int kv_sw128;        // cross K/V tiles land 128B-swizzled (16-byte chunk c of row r sits at chunk c ^ (r & 7))
+  int dbg_skip;        // bring-up: bit0 skip cross-attention (+ its producer), bit1 skip the vocabulary phase
+  unsigned* dbg;       // bring-up breadcrumbs in mapped host memory (16 words per CTA), or nullptr
 };
+
+__device__ unsigned* g_dbg = nullptr;  // set by thread 0 of every CTA from Params (read by the watchdogs)
 
 struct Best {
   float v;
@@ -126,13 +131,36 @@ __device__ __forceinline__ float gelu_as(float x) {  // GELU(erf), Abramowitz-St
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+// mbarrier wait with a watchdog that names the waiting site (one line per warp) and traps instead of hanging the GPU
+__device__ __forceinline__ void fd_wait(uint32_t bar, uint32_t parity, int site) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 3000000000LL) {
+      if (g_dbg && ((threadIdx.x & 31) == 0)) {
+        g_dbg[blockIdx.x * 16 + 4 + ((threadIdx.x >> 5) >= N_CWARPS ? (threadIdx.x >> 5) - N_CWARPS : 4)] =
+            0x80000000u | (unsigned)site | (parity << 8) | ((threadIdx.x >> 5) << 16);
+        __threadfence_system();
+      }
+      if ((threadIdx.x & 31) == 0 || threadIdx.x >= N_CTHREADS)
+        printf("kwb200 decode_fused: wait site %d timed out (block %d warp %d parity %u)\n", site, blockIdx.x,
+               threadIdx.x >> 5, parity);
+      __trap();
+    }
+  }
+}
+
 // mbarrier wait that gives up when the CTA's stop flag is raised (free-running producers); true = barrier completed
 __device__ __forceinline__ bool mbar_wait_or_stop(uint32_t bar, uint32_t parity, volatile int* stop) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (*stop) return false;
-    if (clock64() - t0 > 8000000000LL) {
-      printf("kwb200 decode_fused: producer wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    if (clock64() - t0 > 6000000000LL) {
+      if (g_dbg) {
+        g_dbg[blockIdx.x * 16 + 4 + (threadIdx.x >> 5) - N_CWARPS] = 0xA0000000u | (parity << 8);
+        __threadfence_system();
+      }
+      printf("kwb200 decode_fused: producer wait timed out (block %d warp %d)\n", blockIdx.x, threadIdx.x >> 5);
       __trap();
     }
   }
@@ -197,7 +225,7 @@ struct WProd {
   }
   __device__ void drain() {  // every load that was issued has landed before the CTA may exit
     const uint32_t first = it > NSW ? it - NSW : 0;
-    for (uint32_t i = first; i < it; ++i) mbar_wait(c.w_full(i % NSW), (i / NSW) & 1);
+    for (uint32_t i = first; i < it; ++i) fd_wait(c.w_full(i % NSW), (i / NSW) & 1, 11);
   }
 };
 
@@ -219,7 +247,7 @@ __device__ void w_producer(const Params& p, const Ctx& c, volatile int* stop) {
       pl = plan_of(p.g_fc2, cta);
       if (ok && pl.active) ok = w.tile(m + M_W2, p.g_fc2, pl.n0, pl.kb0);
     }
-    if (ok && pos >= p.n_prompt - 1)
+    if (ok && pos >= p.n_prompt - 1 && !(p.dbg_skip & 2))
       for (int t = cta; ok && t < p.g_voc.tiles; t += p.G)
         ok = w.tile(p.maps + p.L * MAPS_PER_LAYER + M_VOCAB, p.g_voc, t * p.g_voc.R, 0);
   }
@@ -231,7 +259,7 @@ __device__ void kv_producer(const Params& p, const Ctx& c, volatile int* stop) {
   uint32_t it = 0;
   const int cta = blockIdx.x, pairs = p.B * p.H;
   const uint32_t bytes = (uint32_t)p.TR * (HD * 2);
-  bool ok = true;
+  bool ok = !(p.dbg_skip & 1);
   for (int pos = 0; ok && pos + 1 < p.max_length; ++pos)
     for (int l = 0; ok && l < p.L; ++l) {
       const CUtensorMap* m = p.maps + l * MAPS_PER_LAYER + M_XKV;
@@ -248,7 +276,7 @@ __device__ void kv_producer(const Params& p, const Ctx& c, volatile int* stop) {
       }
     }
   const uint32_t first = it > NSKV ? it - NSKV : 0;
-  for (uint32_t i = first; i < it; ++i) mbar_wait(c.kv_full(i % NSKV), (i / NSKV) & 1);
+  for (uint32_t i = first; i < it; ++i) fd_wait(c.kv_full(i % NSKV), (i / NSKV) & 1, 12);
 }
 
 // ---- per-thread pipeline counters of the main (barrier-synchronised) warps -----------------------------------------------
@@ -263,7 +291,7 @@ struct Counters {
 __device__ __forceinline__ void a_thread_tile(const Ctx& c, Counters& k, const CUtensorMap* amap, int kb0, int nkb) {
   for (int kb = 0; kb < nkb; ++kb) {
     const int slot = k.a_it % NSA;
-    mbar_wait(c.a_empty(slot), ((k.a_it / NSA) & 1) ^ 1);
+    fd_wait(c.a_empty(slot), ((k.a_it / NSA) & 1) ^ 1, 3);
     mbar_expect_tx(c.a_full(slot), A_SLOT);
     tma_load_2d(c.base + OFF_A + slot * A_SLOT, amap, c.a_full(slot), (kb0 + kb) * BK, 0);
     ++k.a_it;
@@ -272,13 +300,13 @@ __device__ __forceinline__ void a_thread_tile(const Ctx& c, Counters& k, const C
 
 __device__ __forceinline__ void mma_thread_tile(const Ctx& c, Counters& k, uint32_t tmem_base, const GemmCfg& g) {
   const uint32_t buf = k.t_ct & 1;
-  mbar_wait(c.t_empty(buf), ((k.t_ct >> 1) & 1) ^ 1);
+  fd_wait(c.t_empty(buf), ((k.t_ct >> 1) & 1) ^ 1, 4);
   tc_fence_after();
   const uint32_t d_tmem = tmem_base + buf * NB;
   for (int kb = 0; kb < g.nkb; ++kb) {
     const int j = kb % g.kbps, wslot = k.w_ct % NSW, aslot = k.a_ct % NSA;
-    if (j == 0) mbar_wait(c.w_full(wslot), (k.w_ct / NSW) & 1);
-    mbar_wait(c.a_full(aslot), (k.a_ct / NSA) & 1);
+    if (j == 0) fd_wait(c.w_full(wslot), (k.w_ct / NSW) & 1, 5);
+    fd_wait(c.a_full(aslot), (k.a_ct / NSA) & 1, 6);
     tc_fence_after();
     const uint64_t dw = make_desc(c.base + OFF_W + wslot * W_SLOT + j * g.rpad * (BK * 2));
     const uint64_t da = make_desc(c.base + OFF_A + aslot * A_SLOT);
@@ -368,7 +396,7 @@ __device__ void epilogue_tile(const Params& p, const Ctx& c, Counters& k, uint32
                               const GemmCfg& g, const Plan& pl, int kind, const float* bias, int tid, int warp, int lane) {
   const uint32_t buf = k.t_ct & 1;
   const int q = warp & 3, cg = warp >> 2, RP = g.rpad + 1;
-  mbar_wait(c.t_full(buf), (k.t_ct >> 1) & 1);
+  fd_wait(c.t_full(buf), (k.t_ct >> 1) & 1, 7);
   tc_fence_after();
   if (32 * q < g.R) {
     uint32_t r[16];
@@ -511,7 +539,11 @@ __device__ void cross_attn_phase(const Params& p, const Ctx& c, Counters& k, con
   float* s_red = s_q + HD;             // [2 * N_CWARPS]
   float* s_o = s_red + 2 * N_CWARPS;   // [N_CWARPS][64]
   const int pairs = p.B * p.H, d = p.d, S = p.S, sub = lane >> 3, l8 = lane & 7;
-  const int n_part = p.g_dd.S;
+  const int n_part = p.g_dd.S, swz = p.kv_sw128 ? 7 : 0;
+  if (p.dbg_skip & 1) {
+    for (int i = tid; i < p.B * d; i += N_CTHREADS) if (blockIdx.x == 0) p.dattn[i] = __float2bfloat16_rn(0.0f);
+    return;
+  }
   for (int pr = blockIdx.x; pr < pairs; pr += p.G) {
     const int b = pr / p.H, h = pr % p.H;
     if (tid < HD) {  // q = bias + sum of the cross-q projection's K-group partials (fixed order)
@@ -526,12 +558,12 @@ __device__ void cross_attn_phase(const Params& p, const Ctx& c, Counters& k, con
     float lmax = -INFINITY;
     for (int t = 0; t < p.n_kv_tiles; ++t) {
       const int slot = k.kv_ct % NSKV;
-      mbar_wait(c.kv_full(slot), (k.kv_ct / NSKV) & 1);
+      fd_wait(c.kv_full(slot), (k.kv_ct / NSKV) & 1, 8);
       const uint8_t* tile = c.gen + OFF_KV + slot * KV_SLOT;
       const int rows = min(p.TR, S - t * p.TR);
       for (int r = warp * 4 + sub; r < rows; r += N_CWARPS * 4) {
         float kf[8];
-        unpack8(*reinterpret_cast<const uint4*>(tile + r * (HD * 2) + l8 * 16), kf);
+        unpack8(*reinterpret_cast<const uint4*>(tile + r * (HD * 2) + ((l8 ^ (r & swz)) * 16)), kf);
         float acc = 0.0f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], kf[e], acc);
@@ -558,13 +590,13 @@ __device__ void cross_attn_phase(const Params& p, const Ctx& c, Counters& k, con
     for (int e = 0; e < 8; ++e) o[e] = 0.0f;
     for (int t = 0; t < p.n_kv_tiles; ++t) {
       const int slot = k.kv_ct % NSKV;
-      mbar_wait(c.kv_full(slot), (k.kv_ct / NSKV) & 1);
+      fd_wait(c.kv_full(slot), (k.kv_ct / NSKV) & 1, 9);
       const uint8_t* tile = c.gen + OFF_KV + slot * KV_SLOT;
       const int rows = min(p.TR, S - t * p.TR);
       for (int r = warp * 4 + sub; r < rows; r += N_CWARPS * 4) {
         const float pj = s_p[t * p.TR + r];
         float vf[8];
-        unpack8(*reinterpret_cast<const uint4*>(tile + r * (HD * 2) + l8 * 16), vf);
+        unpack8(*reinterpret_cast<const uint4*>(tile + r * (HD * 2) + ((l8 ^ (r & swz)) * 16)), vf);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[e], o[e]);
       }
@@ -635,7 +667,7 @@ __device__ void vocab_epilogue(const Params& p, const Ctx& c, Counters& k, uint3
                                const int* s_bound, int tile, int warp, int lane) {
   const uint32_t buf = k.t_ct & 1;
   const int q = warp & 3, cg = warp >> 2, tb = p.rules.ts_begin;
-  mbar_wait(c.t_full(buf), (k.t_ct >> 1) & 1);
+  fd_wait(c.t_full(buf), (k.t_ct >> 1) & 1, 10);
   tc_fence_after();
   uint32_t r[16];
   tmem_ld16(tmem_base + ((uint32_t)(32 * q) << 16) + buf * NB + 16 * cg, r);
@@ -737,6 +769,7 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, cta = blockIdx.x;
 
   if (tid == 0) {
+    g_dbg = p.dbg;
     for (int s = 0; s < NSW; ++s) { mbar_init(c.w_full(s), 1); mbar_init(c.w_empty(s), 1); }
     for (int s = 0; s < NSKV; ++s) { mbar_init(c.kv_full(s), 1); mbar_init(c.kv_empty(s), N_CWARPS); }
     for (int s = 0; s < NSA; ++s) { mbar_init(c.a_full(s), 1); mbar_init(c.a_empty(s), 1); }
@@ -762,7 +795,10 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
     const bool is_a = warp == A_WARP && lane == 0, is_mma = warp == MMA_WARP && lane == 0, is_c = warp < N_CWARPS;
     const CUtensorMap* gmaps = p.maps + p.L * MAPS_PER_LAYER;
 
+    int crumb = 0;
     auto phase_sync = [&]() {
+      ++crumb;
+      if (tid == 0 && p.dbg) p.dbg[cta * 16] = (unsigned)crumb;
       fence_async_proxy();  // this thread's global writes precede later TMA (async-proxy) reads by any CTA
       named_sync(1, SYNC_THREADS);
       if (tid == 0) {
@@ -774,6 +810,10 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
         do {
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.bar_counter) : "memory");
           if (clock64() - t0 > 8000000000LL) {
+            if (p.dbg) {
+              p.dbg[cta * 16 + 9] = 0xC0000000u | v;
+              __threadfence_system();
+            }
             printf("kwb200 decode_fused: grid barrier timed out (block %d, %u of %u)\n", blockIdx.x, v, bar_target);
             __trap();
           }
@@ -841,7 +881,7 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
           s_bound[tid] = bd;
         }
         if (is_c) named_sync(2, N_CTHREADS);
-        for (int t = cta; t < p.g_voc.tiles; t += p.G) {
+        for (int t = cta; t < p.g_voc.tiles && !(p.dbg_skip & 2); t += p.G) {
           if (is_a) a_thread_tile(c, k, gmaps + M_DA, 0, p.g_voc.nkb);
           else if (is_mma) mma_thread_tile(c, k, tmem_base, p.g_voc);
           else if (is_c) vocab_epilogue(p, c, k, tmem_base, s_st, s_bound, t, warp, lane);
@@ -890,6 +930,7 @@ struct FusedDecode {
   float* vpart = nullptr;
   unsigned* bar_counter = nullptr;
   int* steps_dev = nullptr;
+  unsigned* dbg_host = nullptr;  // mapped pinned memory, 16 words per CTA
   int n_sm = 0;
   bool ok = false;
 };
@@ -921,6 +962,7 @@ void fused_decode_destroy(kw_model* m) {
   cudaFree(f->vpart);
   cudaFree(f->bar_counter);
   cudaFree(f->steps_dev);
+  if (f->dbg_host) cudaFreeHost(f->dbg_host);
   delete f;
   m->fused = nullptr;
 }
@@ -966,7 +1008,9 @@ int fused_decode_prepare(kw_model* m) {
     g.tiles = (V + g.R - 1) / g.R;
   }
   p.L = L; p.d = d; p.H = c.n_heads; p.F = F; p.V = V; p.S = S; p.MT = c.max_target_pos; p.G = G;
-  p.TR = (S % 125 == 0) ? 125 : 128;
+  p.kv_sw128 = getenv("KW_FUSED_KVSW") ? atoi(getenv("KW_FUSED_KVSW")) : 0;
+  p.dbg_skip = getenv("KW_FUSED_SKIP") ? atoi(getenv("KW_FUSED_SKIP")) : 0;
+  p.TR = (S % 120 == 0) ? 120 : 128;  // 8-row multiple: the swizzle pattern of a tile then starts at row phase 0
   p.n_kv_tiles = (S + p.TR - 1) / p.TR;
 
   const size_t es = 2;
@@ -984,7 +1028,7 @@ int fused_decode_prepare(kw_model* m) {
     rc |= map2d(lm + fd::M_WOX, w.wo_x, d, d, d, p.g_dd.R);
     rc |= map2d(lm + fd::M_W1, w.w1, F, d, d, p.g_fc1.R);
     rc |= map2d(lm + fd::M_W2, w.w2, d, F, F, p.g_fc2.R);
-    rc |= map2d(lm + fd::M_XKV, (const char*)m->xkv + l * xkv_stride, c.max_batch * S, 2 * d, 2 * d, p.TR, false);
+    rc |= map2d(lm + fd::M_XKV, (const char*)m->xkv + l * xkv_stride, c.max_batch * S, 2 * d, 2 * d, p.TR, p.kv_sw128 != 0);
     if (rc) return KW_ERR_CUDA;
     fd::LayerP& lp = layers[l];
     lp.ln1_w = w.ln1_w; lp.ln1_b = w.ln1_b; lp.lnx_w = w.lnx_w; lp.lnx_b = w.lnx_b; lp.ln3_w = w.ln3_w; lp.ln3_b = w.ln3_b;
@@ -1009,6 +1053,13 @@ int fused_decode_prepare(kw_model* m) {
   KW_CUDA_OK(cudaMalloc(&f->vpart, (size_t)fd::NB * p.g_voc.tiles * 4 * fd::VP_WORDS * sizeof(float)));
   KW_CUDA_OK(cudaMalloc(&f->bar_counter, 256));
   KW_CUDA_OK(cudaMalloc(&f->steps_dev, 256));
+  if (getenv("KW_FUSED_DEBUG")) {
+    KW_CUDA_OK(cudaHostAlloc(&f->dbg_host, (size_t)G * 16 * sizeof(unsigned), cudaHostAllocMapped));
+    memset(f->dbg_host, 0, (size_t)G * 16 * sizeof(unsigned));
+    unsigned* dptr = nullptr;
+    KW_CUDA_OK(cudaHostGetDevicePointer(&dptr, f->dbg_host, 0));
+    p.dbg = dptr;
+  }
   p.maps = f->d_maps;
   p.layers = f->d_layers;
   p.x = m->dx; p.dqkv = m->dqkv; p.part = f->part; p.vpart = f->vpart;
@@ -1042,8 +1093,22 @@ int fused_decode_pass(kw_model* m, int B, int n_prompt, int max_length, int retu
                                          fd::SMEM_BYTES, st));
   ++g_launches;
   int steps = 0;
-  KW_CUDA_OK(cudaMemcpyAsync(&steps, f->steps_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-  KW_CUDA_OK(cudaStreamSynchronize(st));
+  cudaError_t e = cudaMemcpyAsync(&steps, f->steps_dev, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    if (f->dbg_host) {
+      fprintf(stderr, "kwb200 decode_fused failed (%s); breadcrumbs [cta: phase | wait sites...]:\n", cudaGetErrorString(e));
+      for (int c = 0; c < f->n_sm; ++c) {
+        const unsigned* d = f->dbg_host + c * 16;
+        bool any = false;
+        for (int i = 4; i < 10; ++i) any |= d[i] != 0;
+        if (c < 4 || any)
+          fprintf(stderr, "  cta %3d: phase %u | W %08x KV %08x A %08x MMA %08x compute %08x gridbar %08x\n", c, d[0], d[4], d[5], d[6], d[7], d[8], d[9]);
+      }
+    }
+    set_error("decode_fused: %s", cudaGetErrorString(e));
+    return KW_ERR_CUDA;
+  }
   return steps;
 }
 
