@@ -231,9 +231,12 @@ void kw_debug_gemm_stamps(uint64_t* dev_buffer_16);
 void kw_set_gemm_impl(int32_t impl);
 /* 1: wide GEMMs (M >= 256) use the 2-CTA tcgen05 kernel (cta_group::2, 256 x 256 tiles per CTA pair); 0: 1-CTA kernel. */
 void kw_set_gemm_2cta(int32_t on);
-/* 1 (default): kw_greedy_pass of a bf16 model runs the whole position loop as ONE persistent kernel (LayerNorm + QKV,
- * self-attention with KV append, cross-attention, fused GELU MLP, vocabulary projection with the logits processors and
- * argmax in its epilogue); 0: one kernel per op (the exact-fp32 schedule; A/B reference).  Process-wide. */
+/* Decode schedule of kw_greedy_pass.  0 (default): one kernel per op, chained with programmatic dependent launch.
+ * 1: a bf16 model runs the whole position loop as ONE persistent cooperative kernel (csrc/decode_fused.cu: LayerNorm +
+ * QKV, self-attention with KV append, cross-attention, GELU MLP, vocabulary projection with the logits processors and
+ * argmax in its epilogue, grid barriers between phases) when its shape fits, else falls back; 2: as 1 but an error
+ * instead of the fallback.  Same tokens up to near-ties; opt-in because it measures slower on B200.
+ * Process-wide; initial value from the environment variable KW_DECODE_FUSED. */
 void kw_set_decode_impl(int32_t impl);
 /* counts kernels launched by this library since the last reset (bench.py's gpu_launches) */
 int64_t kw_launch_count(int32_t reset);

@@ -55,9 +55,11 @@ int sample_launch(const float* logits, const unsigned char* flags, const SampleR
 int fused_decode_prepare(kw_model* m);
 int fused_decode_pass(kw_model* m, int B, int n_prompt, int max_length, int return_ts, int* tokens, cudaStream_t st);
 void fused_decode_destroy(kw_model* m);
+// 0 = one kernel per op (default: measured faster), 1 = persistent fused kernel when the model fits,
+// 2 = fused kernel required (error instead of falling back)
 static std::atomic<int> g_decode_impl{[] {
   const char* e = getenv("KW_DECODE_FUSED");
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 0;
 }()};
 
 int gemm(const GemmArgs& g, cudaStream_t st) {
@@ -460,9 +462,14 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
            Ld * B * 2.0 * m->cfg.max_source_pos * dd * es_d + Ld * B * 2.0 * (pos + 1) * dd * es_d;
   };
   ProfScope pass_scope(KW_PROF_DEC_PASS, 0.0, st);
-  // bf16 models: the whole position loop is ONE persistent kernel (decode_fused.cu); the kernel-per-op schedule below is
-  // the exact-fp32 path and the A/B reference (kw_set_decode_impl(0) / KW_DECODE_FUSED=0)
-  if (m->t == KW_BF16 && g_decode_impl.load() != 0 && g_gemm_impl.load() != 1 && fused_decode_prepare(m) == KW_OK) {
+  // bf16 models, opt-in (kw_set_decode_impl(1) / KW_DECODE_FUSED=1): the whole position loop as ONE persistent kernel
+  // (decode_fused.cu).  Token-identical to the schedule below up to near-ties, but measured slower on B200 (its per-phase
+  // latency + grid barrier cost more than a PDL-chained launch; numbers in DESIGN.md §5), so the kernel-per-op schedule
+  // stays the default.
+  const bool want_fused = m->t == KW_BF16 && g_decode_impl.load() != 0 && g_gemm_impl.load() != 1;
+  const int fused_rc = want_fused ? fused_decode_prepare(m) : KW_ERR_UNSUPPORTED;
+  if (want_fused && fused_rc != KW_OK && (g_decode_impl.load() == 2 || getenv("KW_FUSED_REQUIRE"))) return fused_rc;
+  if (fused_rc == KW_OK) {
     const int done = fused_decode_pass(m, B, n_prompt, max_length, return_timestamps, tokens, st);
     if (done < 0) return done;
     for (int pos = 0; pos < done; ++pos) pass_bytes += position_bytes(pos);

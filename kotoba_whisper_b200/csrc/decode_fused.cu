@@ -49,7 +49,7 @@ constexpr int OFF_MISC = OFF_BAR + 8 * N_BARS;  // tmem slot, stop flag, all-fin
 constexpr size_t SMEM_BYTES = 1024 + OFF_MISC + 64;
 constexpr int TMEM_COLS = 128;
 constexpr uint32_t IDESC = make_idesc(128, NB, 0, 0);
-constexpr int MAX_SPLIT = 4, HD = 64, MAX_T = 512, MAX_S = 1536;
+constexpr int MAX_SPLIT = 8, HD = 64, MAX_T = 512, MAX_S = 1536;
 constexpr int VP_WORDS = 5;  // vocabulary partial: best text (value, id), best timestamp (value, id), sum exp(ts - best ts)
 
 struct GemmCfg {
@@ -77,7 +77,7 @@ struct Params {
   const LayerP* layers;     // device array [L]
   int L, B, d, H, F, V, S, MT, G;
   GemmCfg g_qkv, g_dd, g_fc1, g_fc2, g_voc;
-  float *x, *dqkv, *part, *vpart;
+  float *x, *partqkv, *part, *partq, *vpart;  // partqkv [S][64][3d], part / partq [S][64][d]: K-group partial sums
   bf16 *da, *dattn, *dh;
   const bf16* tok_embed;
   const float *dec_pos, *lnf_w, *lnf_b;
@@ -265,8 +265,8 @@ __device__ void kv_producer(const Params& p, const Ctx& c, volatile int* stop) {
       const CUtensorMap* m = p.maps + l * MAPS_PER_LAYER + M_XKV;
       for (int pr = cta; ok && pr < pairs; pr += p.G) {
         const int b = pr / p.H, h = pr % p.H;
-        for (int kv = 0; ok && kv < 2; ++kv)
-          for (int t = 0; t < p.n_kv_tiles; ++t) {
+        for (int t = 0; ok && t < p.n_kv_tiles; ++t)
+          for (int kv = 0; kv < 2; ++kv) {  // tile t of K, then tile t of V: the consumer folds them in together
             const int slot = it % NSKV;
             if (!mbar_wait_or_stop(c.kv_empty(slot), ((it / NSKV) & 1) ^ 1, stop)) { ok = false; break; }
             mbar_expect_tx(c.kv_full(slot), bytes);
@@ -388,10 +388,11 @@ __device__ void row_phase(const Params& p, float* scr, int b, int kind, int pos,
   }
 }
 
-enum EpiKind { EPI_PART, EPI_QKV, EPI_FC1 };
+enum EpiKind { EPI_PART, EPI_PARTQ, EPI_QKV, EPI_FC1 };
 
 // Compute-warp half of one projection tile: accumulator (lane = weight row, column = batch row) -> transposed through
-// shared memory -> coalesced global stores.
+// shared memory (the activation ring: every k-block of the tile has been consumed when the accumulator is complete, and
+// the next activation loads are issued after the phase barrier) -> coalesced global stores.
 __device__ void epilogue_tile(const Params& p, const Ctx& c, Counters& k, uint32_t tmem_base, float* stage,
                               const GemmCfg& g, const Plan& pl, int kind, const float* bias, int tid, int warp, int lane) {
   const uint32_t buf = k.t_ct & 1;
@@ -420,207 +421,194 @@ __device__ void epilogue_tile(const Params& p, const Ctx& c, Counters& k, uint32
     float v = stage[b * RP + f];
     if (kind == EPI_PART) {
       p.part[((size_t)pl.kg * NB + b) * g.N + n] = v;
+    } else if (kind == EPI_PARTQ) {
+      p.partq[((size_t)pl.kg * NB + b) * g.N + n] = v;
     } else if (kind == EPI_QKV) {
-      p.dqkv[(size_t)b * g.N + n] = v + __ldg(bias + n);
+      p.partqkv[((size_t)pl.kg * NB + b) * g.N + n] = v;
     } else {
       p.dh[(size_t)b * g.N + n] = __float2bfloat16_rn(gelu_as(v + __ldg(bias + n)));
     }
   }
 }
 
-// Self-attention for one decoder position: 4 groups of 128 threads, one (batch, head) pair at a time per group.
-// q | k | v (fp32, bias added) come from dqkv; the new k / v row is appended to the preallocated cache first.
-__device__ void self_attn_phase(const Params& p, const LayerP& L, float* scr, int pos, int tid, int warp, int lane) {
-  const int grp = warp >> 2, gtid = tid & 127, gw = warp & 3, sub = lane >> 3, l8 = lane & 7;
-  float* s_p = scr + grp * (MAX_T + 8 + 4 * HD);
-  float* s_red = s_p + MAX_T;
-  float* s_o = s_red + 8;
-  const int pairs = p.B * p.H, d = p.d, n = pos + 1;
-  for (int pr = blockIdx.x * 4 + grp; pr < pairs; pr += 4 * p.G) {
-    const int b = pr / p.H, h = pr % p.H;
-    const float* row = p.dqkv + (size_t)b * 3 * d;
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float LOG2E = 1.4426950408889634f;
+
+// Running soft-max state of one 8-lane sub-group (each lane: 8 of the 64 output dims): fold in one key / value row.
+// Scores are in log2 units (q is pre-multiplied by log2 e), so exp is a bare ex2.
+__device__ __forceinline__ void online_row(float& m, float& l, float* o, float s, const float* vf) {
+  const float mn = fmaxf(m, s), corr = ex2f(m - mn), pe = ex2f(s - mn);
+  l = fmaf(l, corr, pe);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o[e] = fmaf(o[e], corr, pe * vf[e]);
+  m = mn;
+}
+// merge the states of the 4 sub-groups of a warp (lanes l8, l8 + 8, l8 + 16, l8 + 24 hold the same 8 dims)
+__device__ __forceinline__ void merge_subgroups(float& m, float& l, float* o) {
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, off), l2 = __shfl_xor_sync(0xffffffffu, l, off);
+    const float mn = fmaxf(m, m2);
+    const float c1 = mn == -INFINITY ? 0.0f : ex2f(m - mn), c2 = mn == -INFINITY ? 0.0f : ex2f(m2 - mn);
+    l = l * c1 + l2 * c2;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = o[e] * c1 + __shfl_xor_sync(0xffffffffu, o[e], off) * c2;
+    m = mn;
+  }
+}
+
+// Self-attention for one decoder position, ONE WARP per (batch, head) pair, no block-level synchronisation: the warp adds
+// up the K-group partials of the fused q | k | v projection (+ bias), appends the new k / v row to the preallocated
+// cache, and runs an online soft-max over the <= 448 cached rows, 4 rows per step (8 lanes per row, 16-byte loads),
+// 4 steps in flight.  Rows [row0, row0 + nrows) of the batch; `nw` warps of this CTA take part (wi = 0 .. nw - 1).
+__device__ void self_attn_phase(const Params& p, const LayerP& L, int pos, int row0, int nrows, int wi, int nw, int lane) {
+  const int sub = lane >> 3, l8 = lane & 7, d = p.d, n = pos + 1, n_part = p.g_qkv.S;
+  const int pairs = nrows * p.H;
+  for (int pr = blockIdx.x * nw + wi; pr < pairs; pr += p.G * nw) {
+    const int b = row0 + pr / p.H, h = pr % p.H;
+    // this lane's 8 features of q (all sub-groups), of k (sub-group 0) or of v (sub-group 1)
+    float qf[8], nf[8];
+    const int qcol = h * HD + l8 * 8, ncol = (sub == 0 ? d : 2 * d) + qcol;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { qf[e] = __ldg(L.bqkv + qcol + e); nf[e] = sub < 2 ? __ldg(L.bqkv + ncol + e) : 0.0f; }
+    for (int s = 0; s < n_part; ++s) {
+      const float* row = p.partqkv + ((size_t)s * NB + b) * 3 * d;
+      const float4 a0 = __ldcg(reinterpret_cast<const float4*>(row + qcol)), a1 = __ldcg(reinterpret_cast<const float4*>(row + qcol + 4));
+      qf[0] += a0.x; qf[1] += a0.y; qf[2] += a0.z; qf[3] += a0.w; qf[4] += a1.x; qf[5] += a1.y; qf[6] += a1.z; qf[7] += a1.w;
+      if (sub < 2) {
+        const float4 c0 = __ldcg(reinterpret_cast<const float4*>(row + ncol)), c1 = __ldcg(reinterpret_cast<const float4*>(row + ncol + 4));
+        nf[0] += c0.x; nf[1] += c0.y; nf[2] += c0.z; nf[3] += c0.w; nf[4] += c1.x; nf[5] += c1.y; nf[6] += c1.z; nf[7] += c1.w;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qf[e] *= LOG2E;
     bf16* kp = L.self_k + ((size_t)b * p.H + h) * p.MT * HD;
     bf16* vp = L.self_v + ((size_t)b * p.H + h) * p.MT * HD;
-    if (gtid < HD) kp[(size_t)pos * HD + gtid] = __float2bfloat16_rn(__ldcg(row + d + h * HD + gtid));
-    else vp[(size_t)pos * HD + (gtid - HD)] = __float2bfloat16_rn(__ldcg(row + 2 * d + h * HD + (gtid - HD)));
-    float qf[8];
-    {
-      const float4 a = __ldcg(reinterpret_cast<const float4*>(row + h * HD + l8 * 8));
-      const float4 bq = __ldcg(reinterpret_cast<const float4*>(row + h * HD + l8 * 8 + 4));
-      qf[0] = a.x; qf[1] = a.y; qf[2] = a.z; qf[3] = a.w; qf[4] = bq.x; qf[5] = bq.y; qf[6] = bq.z; qf[7] = bq.w;
+    if (sub < 2) {
+      uint4 pk;
+      pk.x = pack_bf16(nf[0], nf[1]); pk.y = pack_bf16(nf[2], nf[3]); pk.z = pack_bf16(nf[4], nf[5]); pk.w = pack_bf16(nf[6], nf[7]);
+      *reinterpret_cast<uint4*>((sub == 0 ? kp : vp) + (size_t)pos * HD + l8 * 8) = pk;
     }
-    named_sync(3 + grp, 128);  // the new k / v row is visible to the group
-    float lmax = -INFINITY;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-      uint4 kr[2];
-      int jj[2];
+    __syncwarp();  // the appended row is visible to the whole warp
+    float m = -INFINITY, l = 0.0f, o[8];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        jj[u] = j0 + (u * 4 + gw) * 4 + sub;
-        if (jj[u] < n) kr[u] = *reinterpret_cast<const uint4*>(kp + (size_t)jj[u] * HD + l8 * 8);
+    for (int e = 0; e < 8; ++e) o[e] = 0.0f;
+    constexpr int SU = 3;  // row steps in flight per sub-group (6 x 16-byte loads per lane)
+    for (int j0 = 0; j0 < n; j0 += 4 * SU) {
+      uint4 kr[SU], vr[SU];
+#pragma unroll
+      for (int u = 0; u < SU; ++u) {
+        const int j = j0 + u * 4 + sub;
+        if (j < n) {
+          kr[u] = *reinterpret_cast<const uint4*>(kp + (size_t)j * HD + l8 * 8);
+          vr[u] = *reinterpret_cast<const uint4*>(vp + (size_t)j * HD + l8 * 8);
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float acc = 0.0f;
-        if (jj[u] < n) {
-          float kf[8];
+      for (int u = 0; u < SU; ++u) {
+        const int j = j0 + u * 4 + sub;
+        float kf[8], vf[8], acc = 0.0f;
+        if (j < n) {
           unpack8(kr[u], kf);
+          unpack8(vr[u], vf);
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], kf[e], acc);
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (jj[u] < n) {
-          if (l8 == 0) s_p[jj[u]] = acc;
-          lmax = fmaxf(lmax, acc);
-        }
+        if (j < n) online_row(m, l, o, acc, vf);
       }
     }
-    lmax = warp_max(lmax);
-    if (lane == 0) s_red[gw] = lmax;
-    named_sync(3 + grp, 128);
-    const float mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-    float lsum = 0.0f;
-    for (int j = gtid; j < n; j += 128) {
-      const float e = __expf(s_p[j] - mx);
-      s_p[j] = e;
-      lsum += e;
-    }
-    lsum = warp_sum(lsum);
-    if (lane == 0) s_red[4 + gw] = lsum;
-    named_sync(3 + grp, 128);
-    const float inv = 1.0f / (s_red[4] + s_red[5] + s_red[6] + s_red[7]);
-    float o[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = 0.0f;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-      uint4 vr[2];
-      int jj[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        jj[u] = j0 + (u * 4 + gw) * 4 + sub;
-        if (jj[u] < n) vr[u] = *reinterpret_cast<const uint4*>(vp + (size_t)jj[u] * HD + l8 * 8);
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (jj[u] < n) {
-          const float pj = s_p[jj[u]];
-          float vf[8];
-          unpack8(vr[u], vf);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[e], o[e]);
-        }
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
-      o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
-    }
+    merge_subgroups(m, l, o);
     if (sub == 0) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s_o[gw * HD + l8 * 8 + e] = o[e];
+      const float inv = 1.0f / l;
+      uint4 pk;
+      pk.x = pack_bf16(o[0] * inv, o[1] * inv); pk.y = pack_bf16(o[2] * inv, o[3] * inv);
+      pk.z = pack_bf16(o[4] * inv, o[5] * inv); pk.w = pack_bf16(o[6] * inv, o[7] * inv);
+      *reinterpret_cast<uint4*>(p.dattn + (size_t)b * d + h * HD + l8 * 8) = pk;
     }
-    named_sync(3 + grp, 128);
-    if (gtid < HD)
-      p.dattn[(size_t)b * d + h * HD + gtid] =
-          __float2bfloat16_rn((s_o[gtid] + s_o[HD + gtid] + s_o[2 * HD + gtid] + s_o[3 * HD + gtid]) * inv);
-    named_sync(3 + grp, 128);  // scratch free for the next pair
   }
 }
 
-// Cross-attention for one decoder position: the CTA's (batch, head) pairs one after the other, all 16 compute warps on
-// the K / V tiles the producer warp streams through the ring.
-__device__ void cross_attn_phase(const Params& p, const Ctx& c, Counters& k, const LayerP& L, float* scr, int tid,
-                                 int warp, int lane) {
-  float* s_p = scr;                    // [MAX_S] scores / probabilities
-  float* s_q = s_p + MAX_S;            // [64]
-  float* s_red = s_q + HD;             // [2 * N_CWARPS]
-  float* s_o = s_red + 2 * N_CWARPS;   // [N_CWARPS][64]
-  const int pairs = p.B * p.H, d = p.d, S = p.S, sub = lane >> 3, l8 = lane & 7;
+// Cross-attention for one decoder position over rows [row0, row0 + nrows) of the batch: this CTA's (batch, head) pairs
+// one after the other, `nw` warps (wi = 0 .. nw - 1, named barrier `bar`) on the K / V tiles the producer warp streams
+// through the ring (tile t of K, then tile t of V).  Online soft-max per 8-lane sub-group — no block-wide pass over the
+// scores — and one merge of the warps' states per pair.
+__device__ void cross_attn_phase(const Params& p, const Ctx& c, Counters& k, const LayerP& L, float* scr, bf16* out,
+                                 int row0, int nrows, int wi, int nw, int lane, int bar) {
+  float* s_q = scr;              // [64]
+  float* s_m = s_q + HD;         // [nw]
+  float* s_l = s_m + N_CWARPS;   // [nw]
+  float* s_o = s_l + N_CWARPS;   // [nw][64]
+  const int xtid = wi * 32 + lane, nthr = nw * 32;
+  const int pairs = nrows * p.H, d = p.d, S = p.S, sub = lane >> 3, l8 = lane & 7;
   const int n_part = p.g_dd.S, swz = p.kv_sw128 ? 7 : 0;
   if (p.dbg_skip & 1) {
-    for (int i = tid; i < p.B * d; i += N_CTHREADS) if (blockIdx.x == 0) p.dattn[i] = __float2bfloat16_rn(0.0f);
+    for (int i = xtid; i < p.B * d; i += nthr) if (blockIdx.x == 0) out[i] = __float2bfloat16_rn(0.0f);
     return;
   }
   for (int pr = blockIdx.x; pr < pairs; pr += p.G) {
-    const int b = pr / p.H, h = pr % p.H;
-    if (tid < HD) {  // q = bias + sum of the cross-q projection's K-group partials (fixed order)
-      float q = __ldg(L.bq_x + h * HD + tid);
-      for (int s = 0; s < n_part; ++s) q += __ldcg(p.part + ((size_t)s * NB + b) * d + h * HD + tid);
-      s_q[tid] = q;
+    const int b = row0 + pr / p.H, h = pr % p.H;
+    if (xtid < HD) {  // q = bias + sum of the cross-q projection's K-group partials (fixed order), in log2 units
+      float q = __ldg(L.bq_x + h * HD + xtid);
+      for (int s = 0; s < n_part; ++s) q += __ldcg(p.partq + ((size_t)s * NB + b) * d + h * HD + xtid);
+      s_q[xtid] = q * LOG2E;
     }
-    named_sync(2, N_CTHREADS);
+    named_sync(bar, nthr);
     float qf[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) qf[e] = s_q[l8 * 8 + e];
-    float lmax = -INFINITY;
+    float m = -INFINITY, l = 0.0f, o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.0f;
     for (int t = 0; t < p.n_kv_tiles; ++t) {
-      const int slot = k.kv_ct % NSKV;
-      fd_wait(c.kv_full(slot), (k.kv_ct / NSKV) & 1, 8);
-      const uint8_t* tile = c.gen + OFF_KV + slot * KV_SLOT;
+      const int slot_k = k.kv_ct % NSKV, slot_v = (k.kv_ct + 1) % NSKV;
+      fd_wait(c.kv_full(slot_k), (k.kv_ct / NSKV) & 1, 8);
+      fd_wait(c.kv_full(slot_v), ((k.kv_ct + 1) / NSKV) & 1, 9);
+      const uint8_t* tk = c.gen + OFF_KV + slot_k * KV_SLOT;
+      const uint8_t* tv = c.gen + OFF_KV + slot_v * KV_SLOT;
       const int rows = min(p.TR, S - t * p.TR);
-      for (int r = warp * 4 + sub; r < rows; r += N_CWARPS * 4) {
-        float kf[8];
-        unpack8(*reinterpret_cast<const uint4*>(tile + r * (HD * 2) + ((l8 ^ (r & swz)) * 16)), kf);
+      for (int r = wi * 4 + sub; r < rows; r += nw * 4) {
+        const int off = r * (HD * 2) + ((l8 ^ (r & swz)) * 16);
+        float kf[8], vf[8];
+        unpack8(*reinterpret_cast<const uint4*>(tk + off), kf);
+        unpack8(*reinterpret_cast<const uint4*>(tv + off), vf);
         float acc = 0.0f;
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc = fmaf(qf[e], kf[e], acc);
         acc += __shfl_xor_sync(0xffffffffu, acc, 4);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (l8 == 0) s_p[t * p.TR + r] = acc;
-        lmax = fmaxf(lmax, acc);
+        online_row(m, l, o, acc, vf);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(c.kv_empty(slot));
-      ++k.kv_ct;
+      if (lane == 0) { mbar_arrive(c.kv_empty(slot_k)); mbar_arrive(c.kv_empty(slot_v)); }
+      k.kv_ct += 2;
     }
-    const float mx = block_max(lmax, s_red, warp, lane);  // (its barriers also publish s_p)
-    float lsum = 0.0f;
-    for (int j = tid; j < S; j += N_CTHREADS) {
-      const float e = __expf(s_p[j] - mx);
-      s_p[j] = e;
-      lsum += e;
-    }
-    const float inv = 1.0f / block_sum(lsum, s_red + N_CWARPS, warp, lane);
-    float o[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = 0.0f;
-    for (int t = 0; t < p.n_kv_tiles; ++t) {
-      const int slot = k.kv_ct % NSKV;
-      fd_wait(c.kv_full(slot), (k.kv_ct / NSKV) & 1, 9);
-      const uint8_t* tile = c.gen + OFF_KV + slot * KV_SLOT;
-      const int rows = min(p.TR, S - t * p.TR);
-      for (int r = warp * 4 + sub; r < rows; r += N_CWARPS * 4) {
-        const float pj = s_p[t * p.TR + r];
-        float vf[8];
-        unpack8(*reinterpret_cast<const uint4*>(tile + r * (HD * 2) + ((l8 ^ (r & swz)) * 16)), vf);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = fmaf(pj, vf[e], o[e]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(c.kv_empty(slot));
-      ++k.kv_ct;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      o[e] += __shfl_xor_sync(0xffffffffu, o[e], 8);
-      o[e] += __shfl_xor_sync(0xffffffffu, o[e], 16);
-    }
+    merge_subgroups(m, l, o);
     if (sub == 0) {
+      if (l8 == 0) { s_m[wi] = m; s_l[wi] = l; }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s_o[warp * HD + l8 * 8 + e] = o[e];
+      for (int e = 0; e < 8; ++e) s_o[wi * HD + l8 * 8 + e] = o[e];
     }
-    named_sync(2, N_CTHREADS);
-    if (tid < HD) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int w = 0; w < N_CWARPS; ++w) acc += s_o[w * HD + tid];
-      p.dattn[(size_t)b * d + h * HD + tid] = __float2bfloat16_rn(acc * inv);
+    named_sync(bar, nthr);
+    if (xtid < HD) {
+      float mx = s_m[0];
+      for (int w = 1; w < nw; ++w) mx = fmaxf(mx, s_m[w]);
+      float lt = 0.0f, acc = 0.0f;
+      for (int w = 0; w < nw; ++w) {
+        const float cw = s_m[w] == -INFINITY ? 0.0f : ex2f(s_m[w] - mx);
+        lt = fmaf(s_l[w], cw, lt);
+        acc = fmaf(s_o[w * HD + xtid], cw, acc);
+      }
+      out[(size_t)b * d + h * HD + xtid] = __float2bfloat16_rn(acc / lt);
     }
-    named_sync(2, N_CTHREADS);  // scratch free for the next pair
+    named_sync(bar, nthr);  // scratch free for the next pair
   }
 }
 
@@ -796,9 +784,28 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
     const CUtensorMap* gmaps = p.maps + p.L * MAPS_PER_LAYER;
 
     int crumb = 0;
-    auto phase_sync = [&]() {
+    // bring-up timing (KW_FUSED_DEBUG): CTA 0 / thread 0 splits its time per phase kind into work (barrier exit -> next
+    // barrier entry) and barrier (entry -> exit); written behind the breadcrumbs at kernel end
+    constexpr int NPK = 11;
+    unsigned long long acc_work[NPK], acc_bar[NPK], t_mark = 0;
+    unsigned acc_n[NPK];
+#ifndef KW_FD_TIMING
+#define KW_FD_TIMING 0  // build with KW_NVCC_EXTRA=-DKW_FD_TIMING=1 for the per-phase timing table (costs registers)
+#endif
+    const bool timing = KW_FD_TIMING && p.dbg != nullptr && tid == 0 && cta == 0;
+    if (timing) {
+      for (int i = 0; i < NPK; ++i) { acc_work[i] = 0; acc_bar[i] = 0; acc_n[i] = 0; }
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_mark));
+    }
+    auto phase_sync = [&](int pk) {
       ++crumb;
       if (tid == 0 && p.dbg) p.dbg[cta * 16] = (unsigned)crumb;
+      unsigned long long t_in = 0;
+      if (timing) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_in));
+        acc_work[pk] += t_in - t_mark;
+        acc_n[pk] += 1;
+      }
       fence_async_proxy();  // this thread's global writes precede later TMA (async-proxy) reads by any CTA
       named_sync(1, SYNC_THREADS);
       if (tid == 0) {
@@ -822,22 +829,26 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
       }
       named_sync(1, SYNC_THREADS);
       fence_async_proxy();
+      if (timing) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_mark));
+        acc_bar[pk] += t_mark - t_in;
+      }
     };
     // one projection phase; amap = activation operand, kind / bias = epilogue
-    auto gemm_phase = [&](const GemmCfg& g, const CUtensorMap* amap, int kind, const float* bias) {
+    auto gemm_phase = [&](const GemmCfg& g, const CUtensorMap* amap, int kind, const float* bias, int pk) {
       const Plan pl = plan_of(g, cta);
       if (pl.active) {
         if (is_a) a_thread_tile(c, k, amap, pl.kb0, g.nkb);
         else if (is_mma) mma_thread_tile(c, k, tmem_base, g);
-        else if (is_c) epilogue_tile(p, c, k, tmem_base, scr, g, pl, kind, bias, tid, warp, lane);
+        else if (is_c) epilogue_tile(p, c, k, tmem_base, reinterpret_cast<float*>(c.gen + OFF_A), g, pl, kind, bias, tid, warp, lane);
       }
       __syncwarp();
-      phase_sync();
+      phase_sync(pk);
     };
 
     // prologue: embedding + first LayerNorm of position 0
     if (is_c && cta < p.B) row_phase(p, scr, cta, ROW_EMBED, 0, nullptr, 0, p.layers[0].ln1_w, p.layers[0].ln1_b, tid, warp, lane);
-    phase_sync();
+    phase_sync(0);
 
     int steps = 0;
     for (int pos = 0; pos + 1 < p.max_length; ++pos) {
@@ -849,28 +860,28 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
         if (l > 0) {
           if (is_c && cta < p.B)
             row_phase(p, scr, cta, ROW_RES, pos, p.layers[l - 1].b2, p.g_fc2.S, L.ln1_w, L.ln1_b, tid, warp, lane);
-          phase_sync();
+          phase_sync(0);
         }
-        gemm_phase(p.g_qkv, gmaps + M_DA, EPI_QKV, L.bqkv);
-        if (is_c) self_attn_phase(p, L, scr, pos, tid, warp, lane);
-        phase_sync();
-        gemm_phase(p.g_dd, gmaps + M_DATTN, EPI_PART, nullptr);
+        gemm_phase(p.g_qkv, gmaps + M_DA, EPI_QKV, L.bqkv, 1);
+        if (is_c) self_attn_phase(p, L, pos, 0, p.B, warp, N_CWARPS, lane);
+        phase_sync(2);
+        gemm_phase(p.g_dd, gmaps + M_DATTN, EPI_PART, nullptr, 3);
         if (is_c && cta < p.B) row_phase(p, scr, cta, ROW_RES, pos, L.bo, p.g_dd.S, L.lnx_w, L.lnx_b, tid, warp, lane);
-        phase_sync();
-        gemm_phase(p.g_dd, gmaps + M_DA, EPI_PART, nullptr);
-        if (is_c) cross_attn_phase(p, c, k, L, scr, tid, warp, lane);
-        phase_sync();
-        gemm_phase(p.g_dd, gmaps + M_DATTN, EPI_PART, nullptr);
+        phase_sync(0);
+        gemm_phase(p.g_dd, gmaps + M_DA, EPI_PARTQ, nullptr, 4);
+        if (is_c) cross_attn_phase(p, c, k, L, scr, p.dattn, 0, p.B, warp, N_CWARPS, lane, 2);
+        phase_sync(5);
+        gemm_phase(p.g_dd, gmaps + M_DATTN, EPI_PART, nullptr, 6);
         if (is_c && cta < p.B) row_phase(p, scr, cta, ROW_RES, pos, L.bo_x, p.g_dd.S, L.ln3_w, L.ln3_b, tid, warp, lane);
-        phase_sync();
-        gemm_phase(p.g_fc1, gmaps + M_DA, EPI_FC1, L.b1);
-        gemm_phase(p.g_fc2, gmaps + M_DH, EPI_PART, nullptr);
+        phase_sync(0);
+        gemm_phase(p.g_fc1, gmaps + M_DA, EPI_FC1, L.b1, 7);
+        gemm_phase(p.g_fc2, gmaps + M_DH, EPI_PART, nullptr, 8);
       }
       ++steps;
       if (sample) {
         if (is_c && cta < p.B)
           row_phase(p, scr, cta, ROW_RES, pos, p.layers[p.L - 1].b2, p.g_fc2.S, p.lnf_w, p.lnf_b, tid, warp, lane);
-        phase_sync();
+        phase_sync(0);
         // vocabulary projection: tiles cta, cta + G, ...; per-row rule state first (every CTA, from the token history)
         int* s_st = reinterpret_cast<int*>(scr);
         int* s_bound = s_st + NB;
@@ -887,13 +898,13 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
           else if (is_c) vocab_epilogue(p, c, k, tmem_base, s_st, s_bound, t, warp, lane);
         }
         __syncwarp();
-        phase_sync();
+        phase_sync(9);
         if (is_c && cta < p.B) {
           combine_phase(p, scr, cta, pos, tid, warp, lane);
           if (pos + 2 < p.max_length)
             row_phase(p, scr, cta, ROW_EMBED, pos + 1, nullptr, 0, p.layers[0].ln1_w, p.layers[0].ln1_b, tid, warp, lane);
         }
-        phase_sync();
+        phase_sync(10);
         // all rows finished -> the pass is over (GenerationMixin stops when unfinished_sequences.max() == 0)
         if (tid == 0) {
           int all = 1;
@@ -905,9 +916,15 @@ __global__ void __launch_bounds__(THREADS, 1) dec_fused_kernel(const __grid_cons
       } else {
         if (is_c && cta < p.B)
           row_phase(p, scr, cta, ROW_EMBED, pos + 1, nullptr, 0, p.layers[0].ln1_w, p.layers[0].ln1_b, tid, warp, lane);
-        phase_sync();
+        phase_sync(10);
       }
     }
+    if (timing)
+      for (int i = 0; i < NPK; ++i) {
+        p.dbg[gridDim.x * 16 + i * 3] = (unsigned)(acc_work[i] / 1000);
+        p.dbg[gridDim.x * 16 + i * 3 + 1] = (unsigned)(acc_bar[i] / 1000);
+        p.dbg[gridDim.x * 16 + i * 3 + 2] = acc_n[i];
+      }
     if (tid == 0) {
       *s_stop = 1;
       if (cta == 0) *p.steps_out = steps;
@@ -927,6 +944,8 @@ struct FusedDecode {
   CUtensorMap* d_maps = nullptr;
   fd::LayerP* d_layers = nullptr;
   float* part = nullptr;
+  float* partq = nullptr;
+  float* partqkv = nullptr;
   float* vpart = nullptr;
   unsigned* bar_counter = nullptr;
   int* steps_dev = nullptr;
@@ -942,15 +961,20 @@ static bool make_cfg(fd::GemmCfg& g, int N, int K, int G, bool partial) {
   const int kb = K / fd::BK;
   g.N = N;
   g.K = K;
-  g.S = (partial && kb >= 8 && kb % fd::MAX_SPLIT == 0 && G >= 2 * fd::MAX_SPLIT) ? fd::MAX_SPLIT : 1;
+  // K-groups: every CTA should see at most ~5-10 k-blocks, so that its activation operand arrives in one TMA round trip
+  g.S = 1;
+  if (partial) {
+    if (kb >= 80 && kb % 8 == 0 && G >= 16) g.S = 8;
+    else if (kb >= 8 && kb % 4 == 0 && G >= 8) g.S = 4;
+  }
   g.n_groups = G / g.S;
   g.R = (N + g.n_groups - 1) / g.n_groups;
   g.rpad = round_up(g.R, 8);
   g.kbps = std::min(128 / g.rpad, 8);
   g.nkb = kb / g.S;
   g.tiles = 0;
-  // the epilogue transposes [batch 64][rpad + 1] floats through the 16 KB scratch area
-  return g.R <= 128 && g.kbps >= 1 && (size_t)(g.rpad + 1) * fd::NB * sizeof(float) <= (size_t)fd::SCRATCH;
+  // the epilogue transposes [batch 64][rpad + 1] floats through the activation ring (idle once the tile's MMAs are done)
+  return g.R <= 128 && g.kbps >= 1 && (size_t)(g.rpad + 1) * fd::NB * sizeof(float) <= (size_t)fd::NSA * fd::A_SLOT;
 }
 
 void fused_decode_destroy(kw_model* m) {
@@ -959,6 +983,8 @@ void fused_decode_destroy(kw_model* m) {
   cudaFree(f->d_maps);
   cudaFree(f->d_layers);
   cudaFree(f->part);
+  cudaFree(f->partq);
+  cudaFree(f->partqkv);
   cudaFree(f->vpart);
   cudaFree(f->bar_counter);
   cudaFree(f->steps_dev);
@@ -982,23 +1008,33 @@ int fused_decode_prepare(kw_model* m) {
   m->fused = f;
   const kw_config& c = m->cfg;
   if (m->t != KW_BF16 || c.d_model % 64 || c.ffn_dim % 64 || c.d_model > 2048 || c.max_batch > fd::NB ||
-      c.max_target_pos > fd::MAX_T || c.max_source_pos > fd::MAX_S)
+      c.max_target_pos > fd::MAX_T || c.max_source_pos > fd::MAX_S) {
+    set_error("decode_fused: model shape / dtype outside the fused kernel's envelope");
     return KW_ERR_UNSUPPORTED;
+  }
   int dev = 0, coop = 0;
   KW_CUDA_OK(cudaGetDevice(&dev));
   KW_CUDA_OK(cudaDeviceGetAttribute(&f->n_sm, cudaDevAttrMultiProcessorCount, dev));
   KW_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-  if (!coop) return KW_ERR_UNSUPPORTED;
+  if (!coop) {
+    set_error("decode_fused: device has no cooperative launch");
+    return KW_ERR_UNSUPPORTED;
+  }
   KW_CUDA_OK(cudaFuncSetAttribute(fd::dec_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fd::SMEM_BYTES));
   int per_sm = 0;
   KW_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fd::dec_fused_kernel, fd::THREADS, fd::SMEM_BYTES));
-  if (per_sm < 1) return KW_ERR_UNSUPPORTED;
+  if (per_sm < 1) {
+    set_error("decode_fused: kernel does not fit one CTA per SM (%d threads, %zu B shared memory)", fd::THREADS, fd::SMEM_BYTES);
+    return KW_ERR_UNSUPPORTED;
+  }
   const int G = f->n_sm, d = c.d_model, F = c.ffn_dim, V = c.vocab_size, S = c.max_source_pos, L = c.dec_layers;
   fd::Params& p = f->p;
   memset(&p, 0, sizeof(p));
-  if (!make_cfg(p.g_qkv, 3 * d, d, G, false) || !make_cfg(p.g_dd, d, d, G, true) || !make_cfg(p.g_fc1, F, d, G, false) ||
-      !make_cfg(p.g_fc2, d, F, G, true))
+  if (!make_cfg(p.g_qkv, 3 * d, d, G, true) || !make_cfg(p.g_dd, d, d, G, true) || !make_cfg(p.g_fc1, F, d, G, false) ||
+      !make_cfg(p.g_fc2, d, F, G, true)) {
+    set_error("decode_fused: no projection tiling for d=%d ffn=%d on %d SMs", d, F, G);
     return KW_ERR_UNSUPPORTED;
+  }
   {  // vocabulary: tiles of R rows walked cta, cta + G, ...; R chosen so that every CTA gets the same number of tiles
     fd::GemmCfg& g = p.g_voc;
     const int per_cta = (V + G * 128 - 1) / (G * 128);
@@ -1050,19 +1086,21 @@ int fused_decode_prepare(kw_model* m) {
   KW_CUDA_OK(cudaMalloc(&f->d_layers, layers.size() * sizeof(fd::LayerP)));
   KW_CUDA_OK(cudaMemcpy(f->d_layers, layers.data(), layers.size() * sizeof(fd::LayerP), cudaMemcpyHostToDevice));
   KW_CUDA_OK(cudaMalloc(&f->part, (size_t)fd::MAX_SPLIT * fd::NB * d * sizeof(float)));
+  KW_CUDA_OK(cudaMalloc(&f->partq, (size_t)fd::MAX_SPLIT * fd::NB * d * sizeof(float)));
+  KW_CUDA_OK(cudaMalloc(&f->partqkv, (size_t)fd::MAX_SPLIT * fd::NB * 3 * d * sizeof(float)));
   KW_CUDA_OK(cudaMalloc(&f->vpart, (size_t)fd::NB * p.g_voc.tiles * 4 * fd::VP_WORDS * sizeof(float)));
   KW_CUDA_OK(cudaMalloc(&f->bar_counter, 256));
   KW_CUDA_OK(cudaMalloc(&f->steps_dev, 256));
   if (getenv("KW_FUSED_DEBUG")) {
-    KW_CUDA_OK(cudaHostAlloc(&f->dbg_host, (size_t)G * 16 * sizeof(unsigned), cudaHostAllocMapped));
-    memset(f->dbg_host, 0, (size_t)G * 16 * sizeof(unsigned));
+    KW_CUDA_OK(cudaHostAlloc(&f->dbg_host, ((size_t)G * 16 + 64) * sizeof(unsigned), cudaHostAllocMapped));
+    memset(f->dbg_host, 0, ((size_t)G * 16 + 64) * sizeof(unsigned));
     unsigned* dptr = nullptr;
     KW_CUDA_OK(cudaHostGetDevicePointer(&dptr, f->dbg_host, 0));
     p.dbg = dptr;
   }
   p.maps = f->d_maps;
   p.layers = f->d_layers;
-  p.x = m->dx; p.dqkv = m->dqkv; p.part = f->part; p.vpart = f->vpart;
+  p.x = m->dx; p.partqkv = f->partqkv; p.part = f->part; p.partq = f->partq; p.vpart = f->vpart;
   p.da = (bf16*)m->da; p.dattn = (bf16*)m->dattn; p.dh = (bf16*)m->dh;
   p.tok_embed = (const bf16*)m->w.tok_embed;
   p.dec_pos = m->w.dec_pos; p.lnf_w = m->w.dec_ln_w; p.lnf_b = m->w.dec_ln_b;
@@ -1108,6 +1146,19 @@ int fused_decode_pass(kw_model* m, int B, int n_prompt, int max_length, int retu
     }
     set_error("decode_fused: %s", cudaGetErrorString(e));
     return KW_ERR_CUDA;
+  }
+  if (f->dbg_host && getenv("KW_FUSED_TIMING")) {
+    static const char* names[11] = {"row (res+LN)", "qkv gemm", "self-attn", "o gemm", "qx gemm", "cross-attn", "ox gemm",
+                                    "fc1 gemm", "fc2 gemm", "vocab gemm", "combine+embed"};
+    const unsigned* t = f->dbg_host + f->n_sm * 16;
+    fprintf(stderr, "decode_fused timing (CTA 0, %d positions, B=%d): phase | work us | barrier us | count | per phase us\n", steps, B);
+    double tot = 0;
+    for (int i = 0; i < 11; ++i) {
+      fprintf(stderr, "  %-14s %8u %8u %6u   %6.2f + %5.2f\n", names[i], t[i * 3], t[i * 3 + 1], t[i * 3 + 2],
+              t[i * 3 + 2] ? (double)t[i * 3] / t[i * 3 + 2] : 0.0, t[i * 3 + 2] ? (double)t[i * 3 + 1] / t[i * 3 + 2] : 0.0);
+      tot += t[i * 3] + t[i * 3 + 1];
+    }
+    fprintf(stderr, "  total %.1f us = %.1f us per position\n", tot, steps ? tot / steps : 0.0);
   }
   return steps;
 }

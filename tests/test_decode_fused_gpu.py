@@ -17,12 +17,12 @@ def _passes(model, lib, mel, prompt, max_length, ts):
     out = {}
     B = mel.shape[0]
     for impl in (1, 0):
-        lib.kw_set_decode_impl(impl)
+        lib.kw_set_decode_impl(2 if impl else 0)  # 2: the fused kernel or an error, never a silent fallback
         model.encode(mel, return_hidden=False)
         lib.kw_launch_count(1)
         out[impl] = model._greedy_pass(B, prompt, max_length, ts)
         out[f"launches{impl}"] = lib.kw_launch_count(0)
-    lib.kw_set_decode_impl(1)
+    lib.kw_set_decode_impl(0)
     return out
 
 
@@ -47,7 +47,7 @@ def _check_near_tie(model, lib, fused, perop, prompt, tol_sigma=6e-3):
             assert gap <= tol_sigma * scale, (b, j, a[j], c[j], gap, scale)
         return worst
     finally:
-        lib.kw_set_decode_impl(1)
+        lib.kw_set_decode_impl(0)
 
 
 @pytest.mark.parametrize("arch", [TINY, TINY80])
@@ -75,10 +75,10 @@ def test_fused_pass_generate_surface_tiny():
     mel = torch.from_numpy(logmel_batch_f64(clips("UGS", 7), 128)).cuda()
     res = {}
     for impl in (1, 0):
-        lib.kw_set_decode_impl(impl)
+        lib.kw_set_decode_impl(2 if impl else 0)
         st = {}
         res[impl] = (model.generate(mel, language="ja", task="transcribe", return_timestamps=True, max_length=48, stats=st), st)
-    lib.kw_set_decode_impl(1)
+    lib.kw_set_decode_impl(0)
     a, b = res[1][0], res[0][0]
     assert a.dtype == torch.long and a.shape[0] == 3
     assert res[1][1]["passes"] >= 1
@@ -97,6 +97,7 @@ def test_fused_pass_matches_per_op_schedule_kotoba():
     mel = torch.cat([base * (1.0 + 0.01 * i) for i in range(16)]).cuda()
     for ts, prompt in ((False, [50258, 50266, 50360, 50364]), (True, [50258, 50266, 50360])):
         r = _passes(model, lib, mel, prompt, 48, ts)
+        assert r["launches1"] < 10 and r["launches0"] > 500, (r["launches1"], r["launches0"])
         same = sum(int(np.array_equal(r[1][b], r[0][b])) for b in range(64))
         model.encode(mel, return_hidden=False)
         worst = _check_near_tie(model, lib, r[1], r[0], prompt)
