@@ -238,6 +238,11 @@ void kw_set_gemm_2cta(int32_t on);
  * instead of the fallback.  Same tokens up to near-ties; opt-in because it measures slower on B200.
  * Process-wide; initial value from the environment variable KW_DECODE_FUSED. */
 void kw_set_decode_impl(int32_t impl);
+/* 1 (default): in kw_decode_step with sample != 0 and no logits_out, a bf16 model's vocabulary projection applies the
+ * three logits processors and the arg-max in its own epilogue (per-warp partials + a one-CTA-per-row combine kernel):
+ * the [B, vocab] fp32 logits are never written or re-read.  0: projection -> fp32 logits -> sample kernel.  Process-wide;
+ * initial value from KW_SAMPLE_FUSED. */
+void kw_set_sample_fused(int32_t on);
 /* counts kernels launched by this library since the last reset (bench.py's gpu_launches) */
 int64_t kw_launch_count(int32_t reset);
 

@@ -62,6 +62,14 @@ static std::atomic<int> g_decode_impl{[] {
   return e ? atoi(e) : 0;
 }()};
 
+int sample_combine_launch(const SampleFuse& sf, int* tokens, int B, int* finished, cudaStream_t st);
+// 1 (default): the decode-time vocabulary projection of a bf16 model runs the logits processors + arg-max in its epilogue
+// (EPI_ARGMAX) instead of writing fp32 logits for sample_kernel; 0: separate kernels (KW_SAMPLE_FUSED=0, A/B reference)
+static std::atomic<int> g_sample_fused{[] {
+  const char* e = getenv("KW_SAMPLE_FUSED");
+  return e ? atoi(e) : 1;
+}()};
+
 int gemm(const GemmArgs& g, cudaStream_t st) {
   const int impl = g_gemm_impl.load();
   if (impl != 1 && g.a_type == KW_BF16 && g.w_type == KW_BF16) {
@@ -133,6 +141,7 @@ const char* kw_version(void) { return "kwb200 0.1 (sm_100a)"; }
 void kw_set_gemm_impl(int32_t impl) { g_gemm_impl.store(impl); }
 void kw_set_gemm_2cta(int32_t on) { gemm_tc_set_2cta(on); }
 void kw_set_decode_impl(int32_t impl) { g_decode_impl.store(impl); }
+void kw_set_sample_fused(int32_t on) { g_sample_fused.store(on); }
 
 void kw_debug_attention_desc(int32_t v_lbo_bytes, int32_t v_sbo_bytes, int32_t v_kstep_bytes) {
   attention_tc_debug(v_lbo_bytes, v_sbo_bytes, v_kstep_bytes);
@@ -231,8 +240,9 @@ int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_ru
   const size_t szA = al(B * S * d * es), szX = al(B * S * d * 4);
   const size_t szSelf = al(L * B * d * cfg->max_target_pos * es), szXkv = al(L * B * S * 2 * d * es);
   const size_t szDec = al(B * d * 4), szDqkv = al(B * 3 * d * 4), szDh = al(B * F * 4), szLog = al(B * V * 4);
+  const size_t szVp = al(B * 4 * ((V + 127) / 128) * 5 * sizeof(float));  // arg-max partials of the fused vocabulary epilogue
   const size_t total = szP + szQ + 3 * szA + szX + 2 * szSelf + szXkv + 4 * szDec + szDqkv + szDh + szLog + al(V) +
-                       al(B * 4);
+                       al(B * 4) + szVp;
   cudaError_t e = cudaMalloc(&m->pool, total);
   if (e != cudaSuccess) {
     set_error("kw_model_create: cudaMalloc(%zu bytes) failed: %s", total, cudaGetErrorString(e));
@@ -250,6 +260,7 @@ int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_ru
   m->dqkv = (float*)take(szDqkv); m->dh = take(szDh); m->logits = (float*)take(szLog);
   m->flags = (unsigned char*)take(al(V));
   m->finished = (int*)take(al(B * 4));
+  m->vpart = (float*)take(szVp);
 
   std::vector<unsigned char> hf(V, 0);
   for (int i = 0; i < rules->n_suppress; ++i) {
@@ -407,6 +418,24 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
   if (!sample && !logits_out) return KW_OK;
   KW_TRY(layernorm(m->dx, m->w.dec_ln_w, m->w.dec_ln_b, m->da, B, c.d_model, m->t, st));
   float* lg = logits_out ? logits_out : m->logits;
+  if (sample && !logits_out && m->t == KW_BF16 && g_sample_fused.load() && g_gemm_impl.load() != 1) {
+    // vocabulary projection with the logits processors + arg-max fused into its epilogue: no logits are materialised
+    KW_REQUIRE(finished, "kw_decode_step: sample requires the finished array");
+    SampleFuse sf;
+    sf.tokens = tokens; sf.ld_tokens = ld_tokens; sf.pos = pos; sf.begin_index = begin_index;
+    sf.return_ts = return_timestamps; sf.flags = m->flags; sf.rules = m->rules; sf.vpart = m->vpart;
+    sf.n_part = 4 * ((c.vocab_size + 127) / 128);
+    GemmArgs g = mk(m->da, c.d_model, m->t, m->w.tok_embed, m->t, nullptr, nullptr, c.vocab_size, KW_F32, B, c.vocab_size,
+                    c.d_model, EPI_ARGMAX);
+    g.sample = &sf;
+    int rc;
+    {
+      ProfScope ps(KW_PROF_DEC_GEMM, gemm_flops(g), st);
+      rc = gemm_tc(g, st);
+    }
+    if (rc == KW_OK) return sample_combine_launch(sf, tokens, B, finished, st);
+    if (rc != KW_ERR_UNSUPPORTED) return rc;  // unsupported shape (small vocabulary): separate kernels below
+  }
   KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, c.d_model, m->t, m->w.tok_embed, m->t, nullptr, lg, c.vocab_size, KW_F32, B, c.vocab_size,
                  c.d_model, EPI_STORE), st));
   if (sample) {

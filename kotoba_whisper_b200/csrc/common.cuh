@@ -123,6 +123,18 @@ enum Epilogue {
   EPI_GELU = 1,      // out = gelu(acc + bias)
   EPI_RESID = 2,     // out(f32) += acc + bias            (residual stream, in place)
   EPI_GELU_POS = 3,  // out(f32) = gelu(acc + bias) + pos[row % pos_period]   (conv2 + sinusoid table)
+  EPI_ARGMAX = 4,    // decode-time vocabulary projection only: no logits leave the kernel — the three Whisper logits
+                     // processors run on the accumulator and every epilogue warp emits arg-max partials (sample_combine)
+};
+
+// Arguments of the fused vocabulary-projection epilogue (EPI_ARGMAX) and of its combine kernel
+struct SampleFuse {
+  const int* tokens;           // [B, ld_tokens] token history (columns <= pos are read)
+  int ld_tokens, pos, begin_index, return_ts;
+  const unsigned char* flags;  // [vocab] bit0 = suppress, bit1 = suppress at begin
+  SampleRules rules;
+  float* vpart;                // [B][n_part][5] partials, n_part = 4 * number of 128-row vocabulary tiles
+  int n_part;
 };
 
 struct GemmArgs {
@@ -134,6 +146,7 @@ struct GemmArgs {
   int M, N, K, lda, ldo, pos_period;
   int epi;
   kw_dtype a_type, w_type, out_type;
+  const SampleFuse* sample;  // EPI_ARGMAX only
 };
 
 int gemm_simt(const GemmArgs& g, cudaStream_t st);

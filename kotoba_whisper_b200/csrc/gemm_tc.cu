@@ -12,6 +12,7 @@
 // Every mbarrier wait carries a clock64 watchdog that traps instead of hanging the GPU if a pipeline bug deadlocks.
 #include <atomic>
 
+#include "sample_rules.cuh"
 #include "tc_common.cuh"
 
 namespace kw {
@@ -39,6 +40,7 @@ struct Params {
   void* out;
   const float* pos;
   int M, N, K, ldo, pos_period, epi, out_bf16;
+  SampleFuse sf;  // EPI_ARGMAX (decode-time vocabulary projection)
 };
 
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
@@ -673,9 +675,68 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     // slot `rank` of the staging buffer of the cluster's CTA 0 (this CTA's own buffer when there is no split)
     const uint32_t my_slot = out_stage_u32 + (uint32_t)rank * (BN * R * 4);
     const uint32_t slot_remote = S > 1 ? mapa_u32(my_slot, 0) : 0u;
+    // EPI_ARGMAX: per-row state of the timestamp rules, derived once per CTA from the token history
+    int* s_st = reinterpret_cast<int*>(out_stage);
+    int* s_bound = s_st + BN;
+    if (R == 128 && p.epi == EPI_ARGMAX) {
+      if (tid < p.M) sr::row_state(p.sf.tokens + (size_t)tid * p.sf.ld_tokens, p.sf.pos, p.sf.begin_index, p.sf.rules.ts_begin,
+                                   s_st + tid, s_bound + tid);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int tcount = 0; tcount < my_tiles; ++tcount) {
       const int t = worker + tcount * n_workers;
       const uint32_t as = tcount & 1;
+      if (R == 128 && p.epi == EPI_ARGMAX) {
+        // Fused logits processors + arg-max: lane = vocabulary row of this warp's 32-row slice, column = batch row.  One
+        // partial (best text, best timestamp, sum of exp over timestamps) per batch row leaves the warp; the 13 MB fp32
+        // logit matrix is never written.
+        mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
+        tc_fence_after();
+        const int v = t * BM + warp * 32 + lane, tb = p.sf.rules.ts_begin;
+        const bool valid = v < p.N;
+        const unsigned f = valid ? p.sf.flags[v] : 1u;
+        const int lo = t * BM + warp * 32;
+        const bool has_text = lo < tb, has_ts = lo + 31 >= tb;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          if (c * 32 >= p.M) break;
+          uint32_t r[32];
+          tmem_ld32(taddr + c * 32, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          sr::Best my_t = {-INFINITY, p.N}, my_s = {-INFINITY, p.N};
+          float my_sum = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int b = c * 32 + j;
+            if (b >= p.M) break;
+            const float xv = __uint_as_float(r[j]);
+            const bool ok = valid && !sr::token_masked(p.sf.rules, p.sf.return_ts, v, f, s_st[b], s_bound[b]);
+            sr::Best bt = {-INFINITY, p.N}, bs = {-INFINITY, p.N};
+            float sum = 0.0f;
+            if (has_text) {
+              const bool on = ok && v < tb;
+              sr::Best cnd = {on ? xv : -INFINITY, on ? v : p.N};
+              bt = sr::warp_best(cnd);
+            }
+            if (has_ts) {
+              const bool on = ok && v >= tb;
+              sr::Best cnd = {on ? xv : -INFINITY, on ? v : p.N};
+              bs = sr::warp_best(cnd);
+              if (p.sf.return_ts && bs.v > -INFINITY) sum = warp_sum(on ? __expf(xv - bs.v) : 0.0f);
+            }
+            if (lane == j) { my_t = bt; my_s = bs; my_sum = sum; }
+          }
+          const int b = c * 32 + lane;
+          if (b < p.M) {
+            float* o = p.sf.vpart + ((size_t)b * p.sf.n_part + t * 4 + warp) * sr::VP_WORDS;
+            o[0] = my_t.v; o[1] = __int_as_float(my_t.i); o[2] = my_s.v; o[3] = __int_as_float(my_s.i); o[4] = my_sum;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(as));
+        continue;
+      }
       // EPI_RESID: this thread's residual groups are requested before the accumulator wait (R = 32: 4 x 16 bytes)
       float4 res[R == 32 ? 4 : 1];
       if (R == 32 && p.epi == EPI_RESID && vec == 4 && rank == 0) {
@@ -794,6 +855,12 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.bias = g.bias; p.out = g.out; p.pos = g.pos;
   p.M = g.M; p.N = g.N; p.K = g.K; p.ldo = g.ldo; p.pos_period = g.pos_period > 0 ? g.pos_period : 1;
   p.epi = g.epi; p.out_bf16 = g.out_type == KW_BF16;
+  memset(&p.sf, 0, sizeof(p.sf));
+  if (g.epi == EPI_ARGMAX) {
+    if (!g.sample || !(g.M <= sk::BN) || g.N <= 8192) return KW_ERR_UNSUPPORTED;  // R = 128 decode-time kernel only
+    if (g.sample->n_part != 4 * ceil_div(g.N, 128)) return KW_ERR_ARG;
+    p.sf = *g.sample;
+  }
   CUtensorMap tmA, tmB;
   if (g.M <= sk::BN && g.epi != EPI_GELU_POS) {  // decode-time shape: weights stream through the 128-row dimension
     // small projections: 32 weight rows per CTA tile -> 4x the CTAs in flight; 40 rows when 32-row tiles would spill

@@ -1,0 +1,68 @@
+// Device-side pieces of the Whisper logits processors shared by the stand-alone sampling kernel, the vocabulary GEMM's
+// fused arg-max epilogue and the combine kernel (HF/generation/logits_process.py:1855-1862, 1898-1902, 1996-2043).
+#pragma once
+#include "common.cuh"
+
+namespace kw {
+namespace sr {
+
+struct Best {
+  float v;
+  int i;
+};
+__device__ __forceinline__ Best better(Best a, Best b) {  // larger value wins; ties -> smaller index (torch.argmax)
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ Best warp_best(Best x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best y;
+    y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+    y.i = __shfl_xor_sync(0xffffffffu, x.i, o);
+    x = better(x, y);
+  }
+  return x;
+}
+
+// Row state of the timestamp rules, re-derived from the token history (exactly what the HF processor derives from
+// input_ids[k, begin_index:]): bit0 at_begin, bit1 last token is a timestamp, bit2 penultimate is a timestamp (or fewer
+// than two sampled), bit3 any timestamp so far; bound = first timestamp id still allowed.
+__device__ __forceinline__ void row_state(const int* trow, int pos, int begin_index, int tb, int* st, int* bound) {
+  const int n = pos + 1 - begin_index;
+  const int last_ts = n >= 1 && trow[pos] >= tb;
+  const int pen_ts = n < 2 || trow[pos - 1] >= tb;
+  int has_ts = 0, ts_last = 0;
+  for (int j = pos; j >= begin_index; --j)
+    if (trow[j] >= tb) {
+      has_ts = 1;
+      ts_last = trow[j];
+      break;
+    }
+  *st = (n == 0 ? 1 : 0) | (last_ts << 1) | (pen_ts << 2) | (has_ts << 3);
+  *bound = (last_ts && !pen_ts) ? ts_last : ts_last + 1;
+}
+
+// f: bit0 = in suppress_tokens, bit1 = in begin_suppress_tokens
+__device__ __forceinline__ bool token_masked(const SampleRules& r, int return_ts, int v, unsigned f, int st, int bound) {
+  const bool at_begin = st & 1, last_ts = st & 2, pen_ts = st & 4, has_ts = st & 8;
+  if (f & 1) return true;
+  if (at_begin && (f & 2)) return true;
+  if (return_ts) {
+    if (v == r.no_ts) return true;
+    if (last_ts) {
+      if (pen_ts) { if (v >= r.ts_begin) return true; }
+      else if (v < r.eos) return true;
+    }
+    if (has_ts && v >= r.ts_begin && v < bound) return true;
+    if (at_begin) {
+      if (v < r.ts_begin) return true;
+      if (r.max_initial >= 0 && v > r.ts_begin + r.max_initial) return true;
+    }
+  }
+  return false;
+}
+
+constexpr int VP_WORDS = 5;  // partial: best text (value, id), best timestamp (value, id), sum exp(ts - best ts)
+
+}  // namespace sr
+}  // namespace kw

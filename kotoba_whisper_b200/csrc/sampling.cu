@@ -204,6 +204,69 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
   }
 }
 
+// Second half of the fused vocabulary projection (EPI_ARGMAX, gemm_tc.cu): one CTA per batch row folds the per-warp
+// partials [n_part][best text (v, id), best timestamp (v, id), sum exp(ts - best ts)] in a fixed order, applies the
+// "timestamps outweigh text" rule and writes the next token / finished flag (GenerationMixin._sample tail).
+constexpr int SC_THREADS = 256;
+__global__ void __launch_bounds__(SC_THREADS)
+sample_combine_kernel(const float* __restrict__ vpart, int n_part, SampleRules r, int* __restrict__ tokens,
+                      int ld_tokens, int pos, int return_ts, int* __restrict__ finished) {
+  __shared__ Best s_t[SC_THREADS / 32], s_s[SC_THREADS / 32];
+  __shared__ float s_sum[SC_THREADS / 32];
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* vp = vpart + (size_t)b * n_part * 5;
+  Best bt = {-INFINITY, r.vocab}, bs = {-INFINITY, r.vocab};
+  for (int i = tid; i < n_part; i += SC_THREADS) {
+    const float* o = vp + (size_t)i * 5;
+    Best t = {o[0], __float_as_int(o[1])}, s2 = {o[2], __float_as_int(o[3])};
+    bt = better(bt, t);
+    bs = better(bs, s2);
+  }
+  bt = warp_best(bt);
+  bs = warp_best(bs);
+  if (lane == 0) { s_t[warp] = bt; s_s[warp] = bs; }
+  __syncthreads();
+  bt = s_t[0];
+  bs = s_s[0];
+  for (int w = 1; w < SC_THREADS / 32; ++w) { bt = better(bt, s_t[w]); bs = better(bs, s_s[w]); }
+  int choice;
+  if (return_ts) {
+    float part = 0.0f;
+    if (bs.v > -INFINITY)
+      for (int i = tid; i < n_part; i += SC_THREADS) {
+        const float* o = vp + (size_t)i * 5;
+        if (o[2] > -INFINITY) part += o[4] * expf(o[2] - bs.v);
+      }
+    part = warp_sum(part);
+    if (lane == 0) s_sum[warp] = part;
+    __syncthreads();
+    float tot = 0.0f;
+    for (int w = 0; w < SC_THREADS / 32; ++w) tot += s_sum[w];
+    const float lse = (bs.v > -INFINITY) ? bs.v + logf(tot) : -INFINITY;
+    choice = (lse > bt.v) ? bs.i : ((bt.v >= bs.v) ? bt.i : bs.i);
+  } else {
+    choice = (bt.v >= bs.v) ? bt.i : bs.i;
+  }
+  if (tid == 0) {
+    if (choice >= r.vocab) choice = 0;
+    int* trow = tokens + (size_t)b * ld_tokens;
+    const int fin = finished[b];
+    const int next = fin ? r.pad : choice;
+    trow[pos + 1] = next;
+    if (next == r.eos) finished[b] = 1;
+  }
+}
+
+int sample_combine_launch(const SampleFuse& sf, int* tokens, int B, int* finished, cudaStream_t st) {
+  KW_CUDA_OK(launch_pdl(PDL_SAMPLE, sample_combine_kernel, dim3(B), dim3(SC_THREADS), 0, st, (const float*)sf.vpart,
+                        sf.n_part, sf.rules, tokens, sf.ld_tokens, sf.pos, sf.return_ts, finished));
+  KW_LAUNCH_OK();
+  ++g_launches;
+  return KW_OK;
+}
+
 int sample_launch(const float* logits, const unsigned char* flags, const SampleRules& r, int* tokens, int ld_tokens,
                   int B, int pos, int begin_index, int return_ts, int* finished, cudaStream_t st) {
   KW_REQUIRE(pos + 1 < ld_tokens && pos + 1 >= begin_index && begin_index >= 1, "sample: pos=%d begin=%d ld=%d", pos,

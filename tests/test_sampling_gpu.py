@@ -48,3 +48,32 @@ def test_sample_kernel_matches_oracle_rules():
                 assert fin.cpu().tolist() == fin_want
                 n_checked += 1
     assert n_checked == 72
+
+
+@pytest.mark.parametrize("ts", [False, True])
+def test_vocab_projection_with_fused_processors_matches_sample_kernel(ts):
+    """EPI_ARGMAX (gemm_tc.cu) + sample_combine vs fp32 logits + sample_kernel: the accumulators are the same bits, so
+    with the same token history both must pick the same token at every position — checked on whole greedy passes
+    (timestamps on: all pairing / monotonicity / initial-timestamp rules and the log-sum-exp comparison are exercised)."""
+    import numpy as np
+    from _gpu_util import build_pair
+    from _synth import TINY, clips
+    from oracle.logmel_ref import logmel_batch_f64
+    from kotoba_whisper_b200 import _lib
+    lib = _lib.load()
+    model, _ = build_pair(TINY, torch.bfloat16, max_batch=8)
+    mel = torch.from_numpy(logmel_batch_f64(clips("UGSGSUG", 31), 128)).cuda()
+    prompt = [50258, 50266, 50360] + ([] if ts else [50364])
+    out = {}
+    try:
+        for fused in (1, 0):
+            lib.kw_set_sample_fused(fused)
+            model.encode(mel, return_hidden=False)
+            lib.kw_launch_count(1)
+            out[fused] = model._greedy_pass(7, prompt, 96, ts)
+            out[f"n{fused}"] = lib.kw_launch_count(0)
+    finally:
+        lib.kw_set_sample_fused(1)
+    assert np.array_equal(out[1], out[0]), [(b, int(np.argmax(out[1][b] != out[0][b]))) for b in range(7)
+                                            if not np.array_equal(out[1][b], out[0][b])]
+    assert out["n1"] == out["n0"]  # same launch count: combine replaces sample, the projection is the same launch
