@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkwb200.so")
+# KW_LIB_VARIANT=timing selects an instrumented build (libkwb200_timing.so, built by `build.py --variant timing ...`)
+LIB_PATH = os.path.join(_HERE, "libkwb200" + ("_" + os.environ["KW_LIB_VARIANT"] if os.environ.get("KW_LIB_VARIANT") else "") + ".so")
 
 KW_F32, KW_BF16 = 0, 1
 PROF_ENC_GEMM, PROF_ENC_ATTN, PROF_XKV_GEMM, PROF_DEC_GEMM, PROF_DEC_CROSS, PROF_LOGMEL, PROF_DEC_PASS = range(7)

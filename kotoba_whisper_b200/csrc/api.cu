@@ -62,7 +62,7 @@ static std::atomic<int> g_decode_impl{[] {
   return e ? atoi(e) : 0;
 }()};
 
-int sample_combine_launch(const SampleFuse& sf, int* tokens, int B, int* finished, cudaStream_t st);
+int sample_combine_launch(const SampleFuse& sf, int* tokens, int B, int* finished, const EmbedNext& en, cudaStream_t st);
 // 1 (default): the decode-time vocabulary projection of a bf16 model runs the logits processors + arg-max in its epilogue
 // (EPI_ARGMAX) instead of writing fp32 logits for sample_kernel; 0: separate kernels (KW_SAMPLE_FUSED=0, A/B reference)
 static std::atomic<int> g_sample_fused{[] {
@@ -239,8 +239,8 @@ int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_ru
   const size_t szQ = al(std::max(B * T2 * d, B * S * F) * es);
   const size_t szA = al(B * S * d * es), szX = al(B * S * d * 4);
   const size_t szSelf = al(L * B * d * cfg->max_target_pos * es), szXkv = al(L * B * S * 2 * d * es);
-  const size_t szDec = al(B * d * 4), szDqkv = al(B * 3 * d * 4), szDh = al(B * F * 4), szLog = al(B * V * 4);
-  const size_t szVp = al(B * 4 * ((V + 127) / 128) * 5 * sizeof(float));  // arg-max partials of the fused vocabulary epilogue
+  const size_t szDec = al(B * d * 4), szDqkv = al(B * 3 * d * 4), szDh = al(B * F * 4), szLog = al(B * (V + 32) * 4);
+  const size_t szVp = al(B * (V / 32 + 1) * sizeof(float2));  // arg-max partials of the fused vocabulary epilogue
   const size_t total = szP + szQ + 3 * szA + szX + 2 * szSelf + szXkv + 4 * szDec + szDqkv + szDh + szLog + al(V) +
                        al(B * 4) + szVp;
   cudaError_t e = cudaMalloc(&m->pool, total);
@@ -379,16 +379,19 @@ int kw_cross_kv(kw_model* m, int32_t B, kw_stream stream) {
   return KW_OK;
 }
 
-static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int B, int pos, cudaStream_t st) {
+// pre_embedded: the residual stream of this position and LayerNorm_1 of layer 0 were already written by the preceding
+// position's sample_combine_kernel (EmbedNext)
+static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int B, int pos, cudaStream_t st,
+                         bool pre_embedded = false) {
   const kw_config& c = m->cfg;
   const kw_dtype t = m->t;
   const int d = c.d_model, S = c.max_source_pos, F = c.ffn_dim, H = c.n_heads, MT = c.max_target_pos;
   const size_t self_stride = (size_t)c.max_batch * d * MT * esize(t);
   const size_t xkv_stride = (size_t)c.max_batch * S * 2 * d * esize(t);
-  KW_TRY(embed(tokens, ld_tokens, pos, m->w.tok_embed, m->w.dec_pos, m->dx, B, d, c.vocab_size, t, st));
+  if (!pre_embedded) KW_TRY(embed(tokens, ld_tokens, pos, m->w.tok_embed, m->w.dec_pos, m->dx, B, d, c.vocab_size, t, st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const kw_dec_layer_weights& w = m->dec[l];
-    KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, t, st));
+    if (!(pre_embedded && l == 0)) KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, t, st));
     KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
     KW_TRY(dec_self_attn(m->dqkv, (char*)m->self_k + l * self_stride, (char*)m->self_v + l * self_stride, m->dattn, B, d,
                          H, MT, pos, t, st));
@@ -407,24 +410,28 @@ static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int 
   return KW_OK;
 }
 
-int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos, int32_t begin_index,
-                   int32_t sample, int32_t return_timestamps, int32_t* finished, float* logits_out, kw_stream stream) {
-  KW_REQUIRE(m && tokens, "kw_decode_step: null argument");
-  KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch && pos >= 0 && pos < m->cfg.max_target_pos && pos < ld_tokens,
-             "kw_decode_step: B=%d pos=%d ld=%d out of range", B, pos, ld_tokens);
-  cudaStream_t st = (cudaStream_t)stream;
+// One decoder position.  pre_embedded: see decode_hidden.  want_next: when the fused vocabulary epilogue runs, let its combine
+// kernel also embed the picked token and apply LayerNorm_1 of layer 0 for position pos + 1; *did_next reports whether
+// that happened (the caller then passes pre_embedded for the next position).
+static int decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos, int32_t begin_index,
+                       int32_t sample, int32_t return_timestamps, int32_t* finished, float* logits_out, cudaStream_t st,
+                       bool pre_embedded, bool want_next, bool* did_next) {
   const kw_config& c = m->cfg;
-  KW_TRY(decode_hidden(m, tokens, ld_tokens, B, pos, st));
+  if (did_next) *did_next = false;
+  KW_TRY(decode_hidden(m, tokens, ld_tokens, B, pos, st, pre_embedded));
   if (!sample && !logits_out) return KW_OK;
   KW_TRY(layernorm(m->dx, m->w.dec_ln_w, m->w.dec_ln_b, m->da, B, c.d_model, m->t, st));
   float* lg = logits_out ? logits_out : m->logits;
   if (sample && !logits_out && m->t == KW_BF16 && g_sample_fused.load() && g_gemm_impl.load() != 1) {
     // vocabulary projection with the logits processors + arg-max fused into its epilogue: no logits are materialised
+    // (only the ~1.5 k timestamp-range logits per row, in the otherwise unused logits buffer)
     KW_REQUIRE(finished, "kw_decode_step: sample requires the finished array");
     SampleFuse sf;
     sf.tokens = tokens; sf.ld_tokens = ld_tokens; sf.pos = pos; sf.begin_index = begin_index;
-    sf.return_ts = return_timestamps; sf.flags = m->flags; sf.rules = m->rules; sf.vpart = m->vpart;
-    sf.n_part = 4 * ((c.vocab_size + 127) / 128);
+    sf.return_ts = return_timestamps; sf.flags = m->flags; sf.rules = m->rules;
+    sf.tail0 = std::max(0, std::min(m->rules.ts_begin, c.vocab_size)) / 32 * 32;
+    sf.vpart = (float2*)m->vpart; sf.n_part = sf.tail0 / 32;
+    sf.tail = m->logits; sf.tail_ld = (c.vocab_size - sf.tail0 + 31) / 32 * 32;
     GemmArgs g = mk(m->da, c.d_model, m->t, m->w.tok_embed, m->t, nullptr, nullptr, c.vocab_size, KW_F32, B, c.vocab_size,
                     c.d_model, EPI_ARGMAX);
     g.sample = &sf;
@@ -433,7 +440,18 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
       ProfScope ps(KW_PROF_DEC_GEMM, gemm_flops(g), st);
       rc = gemm_tc(g, st);
     }
-    if (rc == KW_OK) return sample_combine_launch(sf, tokens, B, finished, st);
+    if (rc == KW_OK) {
+      EmbedNext en;
+      memset(&en, 0, sizeof(en));
+      en.on = want_next && pos + 1 < c.max_target_pos && c.d_model <= 2048;
+      if (en.on) {
+        en.E = m->w.tok_embed; en.P = m->w.dec_pos; en.ln_w = m->dec[0].ln1_w; en.ln_b = m->dec[0].ln1_b;
+        en.x = m->dx; en.da = m->da; en.d = c.d_model;
+      }
+      KW_TRY(sample_combine_launch(sf, tokens, B, finished, en, st));
+      if (did_next) *did_next = en.on != 0;
+      return KW_OK;
+    }
     if (rc != KW_ERR_UNSUPPORTED) return rc;  // unsupported shape (small vocabulary): separate kernels below
   }
   KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, c.d_model, m->t, m->w.tok_embed, m->t, nullptr, lg, c.vocab_size, KW_F32, B, c.vocab_size,
@@ -443,6 +461,15 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
     KW_TRY(sample_launch(lg, m->flags, m->rules, tokens, ld_tokens, B, pos, begin_index, return_timestamps, finished, st));
   }
   return KW_OK;
+}
+
+int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos, int32_t begin_index,
+                   int32_t sample, int32_t return_timestamps, int32_t* finished, float* logits_out, kw_stream stream) {
+  KW_REQUIRE(m && tokens, "kw_decode_step: null argument");
+  KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch && pos >= 0 && pos < m->cfg.max_target_pos && pos < ld_tokens,
+             "kw_decode_step: B=%d pos=%d ld=%d out of range", B, pos, ld_tokens);
+  return decode_step(m, tokens, ld_tokens, B, pos, begin_index, sample, return_timestamps, finished, logits_out,
+                     (cudaStream_t)stream, false, false, nullptr);
 }
 
 int kw_sample(kw_model* m, const float* logits, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos,
@@ -505,9 +532,13 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
     if (g_prof.mask & (1u << KW_PROF_DEC_PASS)) g_prof.work[KW_PROF_DEC_PASS] += pass_bytes;
     return done;
   }
+  bool pre_embedded = false;
   for (int pos = 0; pos + 1 < max_length; ++pos) {
     const int sample = pos >= n_prompt - 1;
-    KW_TRY(kw_decode_step(m, tokens, max_length, B, pos, n_prompt, sample, return_timestamps, m->finished, nullptr, stream));
+    bool did_next = false;
+    KW_TRY(decode_step(m, tokens, max_length, B, pos, n_prompt, sample, return_timestamps, m->finished, nullptr, st,
+                       pre_embedded, pos + 2 < max_length, &did_next));
+    pre_embedded = did_next;
     ++steps;
     pass_bytes += position_bytes(pos);
     const int generated = pos + 2 - n_prompt;  // tokens sampled so far

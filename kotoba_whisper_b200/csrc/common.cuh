@@ -127,14 +127,30 @@ enum Epilogue {
                      // processors run on the accumulator and every epilogue warp emits arg-max partials (sample_combine)
 };
 
-// Arguments of the fused vocabulary-projection epilogue (EPI_ARGMAX) and of its combine kernel
+// Arguments of the fused vocabulary-projection epilogue (EPI_ARGMAX) and of its combine kernel.  Vocabulary rows below
+// tail0 (a multiple of 32, <= the first timestamp id: text ids only) are reduced inside the GEMM to one (best value, id)
+// pair per batch row and 32-row slice; rows >= tail0 (the ~1.5 k timestamp ids and the specials next to them) leave it as
+// raw fp32 logits, because their rules need the whole timestamp range at once.
 struct SampleFuse {
   const int* tokens;           // [B, ld_tokens] token history (columns <= pos are read)
   int ld_tokens, pos, begin_index, return_ts;
   const unsigned char* flags;  // [vocab] bit0 = suppress, bit1 = suppress at begin
   SampleRules rules;
-  float* vpart;                // [B][n_part][5] partials, n_part = 4 * number of 128-row vocabulary tiles
-  int n_part;
+  float2* vpart;               // [B][n_part] (best masked logit, its id as int bits) per 32-row text slice
+  int n_part;                  // tail0 / 32
+  float* tail;                 // [B][tail_ld] raw logits of vocabulary rows tail0 .. vocab - 1
+  int tail0, tail_ld;
+};
+
+// Optional tail of the combine kernel: embedding of the token just picked + the first LayerNorm of decoder layer 0 for the
+// NEXT position (saves the embed and LayerNorm launches at the head of every decoder position of a greedy pass).
+struct EmbedNext {
+  const void* E;      // [vocab, d] bf16 token embedding
+  const float* P;     // [max_target_pos, d] learned positions
+  const float *ln_w, *ln_b;
+  float* x;           // [B, d] residual stream of the next position
+  void* da;           // [B, d] bf16 LayerNorm output (operand of the next position's QKV projection)
+  int d, on;
 };
 
 struct GemmArgs {

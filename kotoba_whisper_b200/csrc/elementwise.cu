@@ -4,6 +4,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "ln_row.cuh"
 
 namespace kw {
 
@@ -78,42 +79,12 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
   const int lane = threadIdx.x & 31;
   const float* xr = x + (size_t)row * d;
   float4 v[NV];
-  float sum = 0.0f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (i * 32 + lane) * 4;
     if (EXACT || c < d) v[i] = *reinterpret_cast<const float4*>(xr + c);
   }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (EXACT || c < d) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-  }
-  const float mean = warp_sum(sum) / (float)d;
-  float sq = 0.0f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (EXACT || c < d) {
-      float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
-      sq += (a * a + b * b) + (cc * cc + dd * dd);
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)d + 1e-5f);
-  T* orow = out + (size_t)row * d;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (EXACT || c < d) {
-      float4 g = __ldg(reinterpret_cast<const float4*>(w + c)), be = __ldg(reinterpret_cast<const float4*>(bias + c));
-      float4 o;
-      o.x = (v[i].x - mean) * rstd * g.x + be.x;
-      o.y = (v[i].y - mean) * rstd * g.y + be.y;
-      o.z = (v[i].z - mean) * rstd * g.z + be.z;
-      o.w = (v[i].w - mean) * rstd * g.w + be.w;
-      st4(orow + c, o);
-    }
-  }
+  ln_row<T, NV, EXACT>(v, w, bias, out + (size_t)row * d, d, lane);
 }
 
 // ---- decoder embedding: x[b] = E[tokens[b, pos]] + P[pos]  (modeling_whisper.py:738, 755-763) -----------------------

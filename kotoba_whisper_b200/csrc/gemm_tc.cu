@@ -679,24 +679,29 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     int* s_st = reinterpret_cast<int*>(out_stage);
     int* s_bound = s_st + BN;
     if (R == 128 && p.epi == EPI_ARGMAX) {
-      if (tid < p.M) sr::row_state(p.sf.tokens + (size_t)tid * p.sf.ld_tokens, p.sf.pos, p.sf.begin_index, p.sf.rules.ts_begin,
-                                   s_st + tid, s_bound + tid);
+      for (int b = warp; b < p.M; b += SK_EPI_WARPS) {  // one warp per batch row, 32 history positions per step
+        int st, bd;
+        sr::row_state_warp(p.sf.tokens + (size_t)b * p.sf.ld_tokens, p.sf.pos, p.sf.begin_index, p.sf.rules.ts_begin,
+                           p.sf.return_ts, lane, &st, &bd);
+        if (lane == 0) { s_st[b] = st; s_bound[b] = bd; }
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     for (int tcount = 0; tcount < my_tiles; ++tcount) {
       const int t = worker + tcount * n_workers;
       const uint32_t as = tcount & 1;
       if (R == 128 && p.epi == EPI_ARGMAX) {
-        // Fused logits processors + arg-max: lane = vocabulary row of this warp's 32-row slice, column = batch row.  One
-        // partial (best text, best timestamp, sum of exp over timestamps) per batch row leaves the warp; the 13 MB fp32
-        // logit matrix is never written.
+        // Fused logits processors + arg-max: lane = vocabulary row of this warp's 32-row slice, column = batch row.  A
+        // slice of text ids (all but the last ~48) is masked in place and reduced to ONE (best value, id) pair per batch
+        // row; the few slices that reach into the timestamp ids leave the kernel as raw fp32 logits (1.5 k per row) —
+        // their rules (pairing, monotonicity, logsumexp-vs-max) need the whole timestamp range and run in
+        // sample_combine_kernel.  The 13 MB fp32 logit matrix is never written.
         mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
         tc_fence_after();
-        const int v = t * BM + warp * 32 + lane, tb = p.sf.rules.ts_begin;
+        const int lo = t * BM + warp * 32, v = lo + lane;
         const bool valid = v < p.N;
-        const unsigned f = valid ? p.sf.flags[v] : 1u;
-        const int lo = t * BM + warp * 32;
-        const bool has_text = lo < tb, has_ts = lo + 31 >= tb;
+        const bool tail = lo >= p.sf.tail0;
+        const unsigned f = (valid && !tail) ? p.sf.flags[v] : 1u;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
@@ -704,34 +709,41 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          sr::Best my_t = {-INFINITY, p.N}, my_s = {-INFINITY, p.N};
-          float my_sum = 0.0f;
+          if (lo >= p.N) continue;  // slice past the end of the vocabulary (last tile)
+          if (tail) {
+            float* o = p.sf.tail + (size_t)(c * 32) * p.sf.tail_ld + (lo - p.sf.tail0) + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (valid && c * 32 + j < p.M) o[(size_t)j * p.sf.tail_ld] = __uint_as_float(r[j]);
+            continue;
+          }
+          // mask, then a transposing butterfly — 16 + 8 + 4 + 2 + 1 exchanges instead of 32 x 5 — leaves column j's best
+          // in lane j
+          float xv[32];
+          int xi[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int b = c * 32 + j;
-            if (b >= p.M) break;
-            const float xv = __uint_as_float(r[j]);
+            const int b = min(c * 32 + j, p.M - 1);
             const bool ok = valid && !sr::token_masked(p.sf.rules, p.sf.return_ts, v, f, s_st[b], s_bound[b]);
-            sr::Best bt = {-INFINITY, p.N}, bs = {-INFINITY, p.N};
-            float sum = 0.0f;
-            if (has_text) {
-              const bool on = ok && v < tb;
-              sr::Best cnd = {on ? xv : -INFINITY, on ? v : p.N};
-              bt = sr::warp_best(cnd);
+            xv[j] = ok ? __uint_as_float(r[j]) : -INFINITY;
+            xi[j] = ok ? v : p.N;
+          }
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) {
+            const bool up = lane & o;
+#pragma unroll
+            for (int j = 0; j < o; ++j) {
+              const float sv = up ? xv[j] : xv[j + o], kv = up ? xv[j + o] : xv[j];
+              const int si = up ? xi[j] : xi[j + o], ki = up ? xi[j + o] : xi[j];
+              sr::Best rcv = {__shfl_xor_sync(0xffffffffu, sv, o), __shfl_xor_sync(0xffffffffu, si, o)};
+              sr::Best kp = {kv, ki};
+              kp = sr::better(kp, rcv);
+              xv[j] = kp.v;
+              xi[j] = kp.i;
             }
-            if (has_ts) {
-              const bool on = ok && v >= tb;
-              sr::Best cnd = {on ? xv : -INFINITY, on ? v : p.N};
-              bs = sr::warp_best(cnd);
-              if (p.sf.return_ts && bs.v > -INFINITY) sum = warp_sum(on ? __expf(xv - bs.v) : 0.0f);
-            }
-            if (lane == j) { my_t = bt; my_s = bs; my_sum = sum; }
           }
           const int b = c * 32 + lane;
-          if (b < p.M) {
-            float* o = p.sf.vpart + ((size_t)b * p.sf.n_part + t * 4 + warp) * sr::VP_WORDS;
-            o[0] = my_t.v; o[1] = __int_as_float(my_t.i); o[2] = my_s.v; o[3] = __int_as_float(my_s.i); o[4] = my_sum;
-          }
+          if (b < p.M) p.sf.vpart[(size_t)b * p.sf.n_part + (lo >> 5)] = make_float2(xv[0], __int_as_float(xi[0]));
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(as));
@@ -858,7 +870,9 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   memset(&p.sf, 0, sizeof(p.sf));
   if (g.epi == EPI_ARGMAX) {
     if (!g.sample || !(g.M <= sk::BN) || g.N <= 8192) return KW_ERR_UNSUPPORTED;  // R = 128 decode-time kernel only
-    if (g.sample->n_part != 4 * ceil_div(g.N, 128)) return KW_ERR_ARG;
+    if (g.sample->tail0 % 32 != 0 || g.sample->n_part != g.sample->tail0 / 32 || g.sample->tail0 > g.N ||
+        g.sample->tail_ld < g.N - g.sample->tail0)
+      return KW_ERR_ARG;
     p.sf = *g.sample;
   }
   CUtensorMap tmA, tmB;

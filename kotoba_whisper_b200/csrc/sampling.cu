@@ -11,6 +11,8 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "ln_row.cuh"
+#include "sample_rules.cuh"
 
 namespace kw {
 
@@ -80,23 +82,16 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
   const float* row = logits + (size_t)b * r.vocab;
   int* trow = tokens + (size_t)b * ld_tokens;
 
-  if (tid == 0) {
-    const int n = pos + 1 - begin_index;  // tokens sampled so far in this pass
-    const int tb = r.ts_begin;
-    int last_ts = n >= 1 && trow[pos] >= tb;
-    int pen_ts = n < 2 || trow[pos - 1] >= tb;
-    int has_ts = 0, ts_last = 0;
-    for (int j = pos; j >= begin_index; --j)
-      if (trow[j] >= tb) {
-        has_ts = 1;
-        ts_last = trow[j];
-        break;
-      }
-    s_state[0] = (n == 0);
-    s_state[1] = last_ts;
-    s_state[2] = pen_ts;
-    s_state[3] = has_ts;
-    s_state[4] = (last_ts && !pen_ts) ? ts_last : ts_last + 1;
+  if (tid < 32) {  // warp 0: row state, 32 history positions per step (sample_rules.cuh)
+    int st, bd;
+    sr::row_state_warp(trow, pos, begin_index, r.ts_begin, return_ts, tid, &st, &bd);
+    if (tid == 0) {
+      s_state[0] = st & 1;
+      s_state[1] = (st >> 1) & 1;
+      s_state[2] = (st >> 2) & 1;
+      s_state[3] = (st >> 3) & 1;
+      s_state[4] = bd;
+    }
   }
   __syncthreads();
   const bool at_begin = s_state[0], last_ts = s_state[1], pen_ts = s_state[2], has_ts = s_state[3];
@@ -204,25 +199,41 @@ sample_kernel(const float* __restrict__ logits, const unsigned char* __restrict_
   }
 }
 
-// Second half of the fused vocabulary projection (EPI_ARGMAX, gemm_tc.cu): one CTA per batch row folds the per-warp
-// partials [n_part][best text (v, id), best timestamp (v, id), sum exp(ts - best ts)] in a fixed order, applies the
-// "timestamps outweigh text" rule and writes the next token / finished flag (GenerationMixin._sample tail).
+// Second half of the fused vocabulary projection (EPI_ARGMAX, gemm_tc.cu): one CTA per batch row folds the text-slice
+// partials in a fixed order, runs the logits processors over the raw tail (timestamp ids and the specials next to them,
+// ~1.5 k logits), applies the "timestamps outweigh text" rule and writes the next token / finished flag
+// (GenerationMixin._sample tail).  With en.on it also prepares the next decoder position: x = E[next] + P[pos + 1] and
+// LayerNorm_1 of decoder layer 0 (modeling_whisper.py:738, 755-763, 468) — bit-identical to embed_kernel + layernorm_kernel.
 constexpr int SC_THREADS = 256;
 __global__ void __launch_bounds__(SC_THREADS)
-sample_combine_kernel(const float* __restrict__ vpart, int n_part, SampleRules r, int* __restrict__ tokens,
-                      int ld_tokens, int pos, int return_ts, int* __restrict__ finished) {
+sample_combine_kernel(const SampleFuse sf, int* __restrict__ tokens, int* __restrict__ finished, const EmbedNext en) {
   __shared__ Best s_t[SC_THREADS / 32], s_s[SC_THREADS / 32];
   __shared__ float s_sum[SC_THREADS / 32];
+  __shared__ int s_state[2], s_next;
   pdl_trigger();
   pdl_wait();
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* vp = vpart + (size_t)b * n_part * 5;
+  const SampleRules& r = sf.rules;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, tb = r.ts_begin;
+  int* trow = tokens + (size_t)b * sf.ld_tokens;
+  if (warp == 0) {
+    int st, bd;
+    sr::row_state_warp(trow, sf.pos, sf.begin_index, tb, sf.return_ts, lane, &st, &bd);
+    if (lane == 0) { s_state[0] = st; s_state[1] = bd; }
+  }
   Best bt = {-INFINITY, r.vocab}, bs = {-INFINITY, r.vocab};
-  for (int i = tid; i < n_part; i += SC_THREADS) {
-    const float* o = vp + (size_t)i * 5;
-    Best t = {o[0], __float_as_int(o[1])}, s2 = {o[2], __float_as_int(o[3])};
+  const float2* vp = sf.vpart + (size_t)b * sf.n_part;
+  for (int i = tid; i < sf.n_part; i += SC_THREADS) {
+    const float2 o = vp[i];
+    Best t = {o.x, __float_as_int(o.y)};
     bt = better(bt, t);
-    bs = better(bs, s2);
+  }
+  __syncthreads();
+  const int st = s_state[0], bound = s_state[1];
+  const float* tl = sf.tail + (size_t)b * sf.tail_ld;
+  for (int v = sf.tail0 + tid; v < r.vocab; v += SC_THREADS) {
+    if (sr::token_masked(r, sf.return_ts, v, sf.flags[v], st, bound)) continue;
+    Best c = {tl[v - sf.tail0], v};
+    if (v < tb) bt = better(bt, c); else bs = better(bs, c);
   }
   bt = warp_best(bt);
   bs = warp_best(bs);
@@ -232,13 +243,12 @@ sample_combine_kernel(const float* __restrict__ vpart, int n_part, SampleRules r
   bs = s_s[0];
   for (int w = 1; w < SC_THREADS / 32; ++w) { bt = better(bt, s_t[w]); bs = better(bs, s_s[w]); }
   int choice;
-  if (return_ts) {
+  if (sf.return_ts) {
+    // logsumexp over the unmasked timestamp logits vs the best text logit (log_softmax's shift cancels on both sides)
     float part = 0.0f;
     if (bs.v > -INFINITY)
-      for (int i = tid; i < n_part; i += SC_THREADS) {
-        const float* o = vp + (size_t)i * 5;
-        if (o[2] > -INFINITY) part += o[4] * expf(o[2] - bs.v);
-      }
+      for (int v = max(tb, sf.tail0) + tid; v < r.vocab; v += SC_THREADS)
+        if (!sr::token_masked(r, sf.return_ts, v, sf.flags[v], st, bound)) part += expf(tl[v - sf.tail0] - bs.v);
     part = warp_sum(part);
     if (lane == 0) s_sum[warp] = part;
     __syncthreads();
@@ -251,17 +261,35 @@ sample_combine_kernel(const float* __restrict__ vpart, int n_part, SampleRules r
   }
   if (tid == 0) {
     if (choice >= r.vocab) choice = 0;
-    int* trow = tokens + (size_t)b * ld_tokens;
     const int fin = finished[b];
     const int next = fin ? r.pad : choice;
-    trow[pos + 1] = next;
+    trow[sf.pos + 1] = next;
     if (next == r.eos) finished[b] = 1;
+    s_next = next;
   }
+  if (!en.on) return;
+  __syncthreads();
+  if (warp != 0) return;
+  const int d = en.d, tok = min(max(s_next, 0), r.vocab - 1);
+  const bf16* e = reinterpret_cast<const bf16*>(en.E) + (size_t)tok * d;
+  const float* pp = en.P + (size_t)(sf.pos + 1) * d;
+  constexpr int NV = 16;  // d <= 2048 (checked at launch)
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < d) {
+      const float4 a = ld4(e + c), q = *reinterpret_cast<const float4*>(pp + c);
+      v[i] = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
+      *reinterpret_cast<float4*>(en.x + (size_t)b * d + c) = v[i];
+    }
+  }
+  ln_row<bf16, NV, false>(v, en.ln_w, en.ln_b, reinterpret_cast<bf16*>(en.da) + (size_t)b * d, d, lane);
 }
 
-int sample_combine_launch(const SampleFuse& sf, int* tokens, int B, int* finished, cudaStream_t st) {
-  KW_CUDA_OK(launch_pdl(PDL_SAMPLE, sample_combine_kernel, dim3(B), dim3(SC_THREADS), 0, st, (const float*)sf.vpart,
-                        sf.n_part, sf.rules, tokens, sf.ld_tokens, sf.pos, sf.return_ts, finished));
+int sample_combine_launch(const SampleFuse& sf, int* tokens, int B, int* finished, const EmbedNext& en, cudaStream_t st) {
+  KW_REQUIRE(!en.on || (en.d % 4 == 0 && en.d <= 2048), "sample_combine: d=%d unsupported", en.d);
+  KW_CUDA_OK(launch_pdl(PDL_SAMPLE, sample_combine_kernel, dim3(B), dim3(SC_THREADS), 0, st, sf, tokens, finished, en));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

@@ -76,4 +76,6 @@ def test_vocab_projection_with_fused_processors_matches_sample_kernel(ts):
         lib.kw_set_sample_fused(1)
     assert np.array_equal(out[1], out[0]), [(b, int(np.argmax(out[1][b] != out[0][b]))) for b in range(7)
                                             if not np.array_equal(out[1][b], out[0][b])]
-    assert out["n1"] == out["n0"]  # same launch count: combine replaces sample, the projection is the same launch
+    # combine replaces sample, and also does the next position's embedding + first LayerNorm: two launches fewer per
+    # sampled position but the last
+    assert out["n0"] - 2 * (96 - len(prompt)) <= out["n1"] < out["n0"], (out["n1"], out["n0"])
