@@ -85,6 +85,24 @@ int gemm(const GemmArgs& g, cudaStream_t st) {
 
 static size_t esize(kw_dtype t) { return t == KW_BF16 ? 2 : 4; }
 
+// The kernels keep per-process state that belongs to ONE device (the > 48 KB shared-memory opt-ins, the SM count, the
+// log-mel tables): the library is one-process-per-GPU by design.  Every entry point that launches work
+// checks that the current device is the one the process first used, instead of failing obscurely on a second GPU.
+static std::atomic<int> g_bound_device{-1};
+static int bound_device_ok(const char* who) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("%s: no CUDA device (this library has no CPU fallback)", who);
+    return KW_ERR_CUDA;
+  }
+  int expect = -1;
+  if (g_bound_device.compare_exchange_strong(expect, dev) || expect == dev) return KW_OK;
+  set_error("%s: this process is bound to CUDA device %d (first use) but device %d is current; run one process per GPU",
+            who, expect, dev);
+  return KW_ERR_ARG;
+}
+
+
 // ---- optional per-category device timing (CUDA events on the launching stream; bench.py's roofline legs) -----------
 struct ProfRec {
   int cat;
@@ -133,6 +151,12 @@ static double gemm_flops(const GemmArgs& g) { return 2.0 * g.M * (double)g.N * g
 using namespace kw;
 
 #include "model.cuh"
+
+#define KW_TRY(expr)           \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != KW_OK) return _rc; \
+  } while (0)
 
 extern "C" {
 
@@ -188,6 +212,7 @@ int64_t kw_launch_count(int32_t reset) {
 
 int kw_logmel(const float* audio, const int32_t* lens, int32_t B, int32_t n_samples, int32_t n_mels, float* out,
               float* clip_max, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_logmel"));
   KW_REQUIRE(audio && out && clip_max, "kw_logmel: null pointer");
   ProfScope ps(KW_PROF_LOGMEL, (double)B * (4.0 * n_samples + 4.0 * n_mels * (n_samples / 160)), (cudaStream_t)stream);
   return logmel_launch(audio, nullptr, lens, B, n_samples, n_mels, out, clip_max, (cudaStream_t)stream);
@@ -195,6 +220,7 @@ int kw_logmel(const float* audio, const int32_t* lens, int32_t B, int32_t n_samp
 
 int kw_logmel_windows(const float* recording, const int64_t* starts, const int32_t* lens, int32_t W, int32_t n_samples,
                       int32_t n_mels, float* out, float* clip_max, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_logmel_windows"));
   KW_REQUIRE(recording && starts && lens && out && clip_max, "kw_logmel_windows: null pointer");
   ProfScope ps(KW_PROF_LOGMEL, (double)W * (4.0 * n_samples + 4.0 * n_mels * (n_samples / 160)), (cudaStream_t)stream);
   return logmel_launch(recording, (const long long*)starts, lens, W, n_samples, n_mels, out, clip_max,
@@ -216,6 +242,7 @@ int kw_mel_filterbank(int32_t n_mels, double* out_host) {
 }
 
 int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_rules* rules, kw_model** out) {
+  KW_TRY(bound_device_ok("kw_model_create"));
   KW_REQUIRE(cfg && w && rules && out, "kw_model_create: null argument");
   KW_REQUIRE(cfg->d_model % 64 == 0 && cfg->n_heads * 64 == cfg->d_model, "kw_model_create: head dim must be 64");
   KW_REQUIRE(cfg->ffn_dim % 16 == 0 && (3 * cfg->n_mels) % 16 == 0, "kw_model_create: ffn / 3*n_mels must be multiples of 16");
@@ -303,18 +330,13 @@ static GemmArgs mk(const void* A, int lda, kw_dtype at, const void* W, kw_dtype 
   return g;
 }
 
-#define KW_TRY(expr)           \
-  do {                         \
-    int _rc = (expr);          \
-    if (_rc != KW_OK) return _rc; \
-  } while (0)
-
 static int gemm_p(int cat, const GemmArgs& g, cudaStream_t st) {
   ProfScope ps(cat, gemm_flops(g), st);
   return gemm(g, st);
 }
 
 int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_encode"));
   KW_REQUIRE(m && mel, "kw_encode: null argument");
   KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch, "kw_encode: B=%d outside [1, max_batch=%d]", B, m->cfg.max_batch);
   cudaStream_t st = (cudaStream_t)stream;
@@ -360,6 +382,7 @@ int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_strea
 }
 
 int kw_set_encoder_output(kw_model* m, const float* enc, int32_t B, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_set_encoder_output"));
   KW_REQUIRE(m && enc && B >= 1 && B <= m->cfg.max_batch, "kw_set_encoder_output: bad arguments");
   KW_TRY(convert_f32_to(enc, m->enc_out, (size_t)B * m->cfg.max_source_pos * m->cfg.d_model, m->t, (cudaStream_t)stream));
   m->enc_B = B;
@@ -367,6 +390,7 @@ int kw_set_encoder_output(kw_model* m, const float* enc, int32_t B, kw_stream st
 }
 
 int kw_cross_kv(kw_model* m, int32_t B, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_cross_kv"));
   KW_REQUIRE(m && B >= 1 && B <= m->enc_B, "kw_cross_kv: B=%d but encoder output holds %d rows", B, m ? m->enc_B : 0);
   const kw_config& c = m->cfg;
   const int d = c.d_model, S = c.max_source_pos;
@@ -430,7 +454,7 @@ static int decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t 
     sf.tokens = tokens; sf.ld_tokens = ld_tokens; sf.pos = pos; sf.begin_index = begin_index;
     sf.return_ts = return_timestamps; sf.flags = m->flags; sf.rules = m->rules;
     sf.tail0 = std::max(0, std::min(m->rules.ts_begin, c.vocab_size)) / 32 * 32;
-    sf.vpart = (float2*)m->vpart; sf.n_part = sf.tail0 / 32;
+    sf.vpart = (float2*)m->vpart; sf.n_part = 2 * ((sf.tail0 + 127) / 128);
     sf.tail = m->logits; sf.tail_ld = (c.vocab_size - sf.tail0 + 31) / 32 * 32;
     GemmArgs g = mk(m->da, c.d_model, m->t, m->w.tok_embed, m->t, nullptr, nullptr, c.vocab_size, KW_F32, B, c.vocab_size,
                     c.d_model, EPI_ARGMAX);
@@ -465,6 +489,7 @@ static int decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t 
 
 int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos, int32_t begin_index,
                    int32_t sample, int32_t return_timestamps, int32_t* finished, float* logits_out, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_decode_step"));
   KW_REQUIRE(m && tokens, "kw_decode_step: null argument");
   KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch && pos >= 0 && pos < m->cfg.max_target_pos && pos < ld_tokens,
              "kw_decode_step: B=%d pos=%d ld=%d out of range", B, pos, ld_tokens);
@@ -474,6 +499,7 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
 
 int kw_sample(kw_model* m, const float* logits, int32_t* tokens, int32_t ld_tokens, int32_t B, int32_t pos,
               int32_t begin_index, int32_t return_timestamps, int32_t* finished, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_sample"));
   KW_REQUIRE(m && logits && tokens && finished, "kw_sample: null argument");
   return sample_launch(logits, m->flags, m->rules, tokens, ld_tokens, B, pos, begin_index, return_timestamps, finished,
                        (cudaStream_t)stream);
@@ -489,6 +515,7 @@ __global__ void fill_prompt_kernel(int* tokens, int ld, int B, const int4 p0, in
 
 int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
                    int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_greedy_pass"));
   KW_REQUIRE(m && prompt && tokens, "kw_greedy_pass: null argument");
   KW_REQUIRE(n_prompt >= 1 && n_prompt <= 4, "kw_greedy_pass: prompt of %d tokens (1..4 supported)", n_prompt);
   KW_REQUIRE(max_length > n_prompt && max_length <= m->cfg.max_target_pos,
@@ -565,6 +592,7 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
 // frozen teacher.  Rows are (b, t)-major; the encoder workspaces double as decoder workspaces (B*T <= B*1500).
 int kw_decoder_forward(kw_model* m, const int32_t* decoder_input_ids, int32_t B, int32_t T, float* logits_out,
                        kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_decoder_forward"));
   KW_REQUIRE(m && decoder_input_ids && logits_out, "kw_decoder_forward: null argument");
   KW_REQUIRE(B >= 1 && B <= m->enc_B, "kw_decoder_forward: B=%d but encoder output holds %d rows", B, m->enc_B);
   KW_REQUIRE(T >= 1 && T <= m->cfg.max_target_pos, "kw_decoder_forward: T=%d outside [1, %d]", T, m->cfg.max_target_pos);
@@ -613,6 +641,7 @@ int kw_decoder_forward(kw_model* m, const int32_t* decoder_input_ids, int32_t B,
 int kw_attention(const void* q, const void* k, const void* v, void* out, int32_t B, int32_t H, int32_t Tq, int32_t Tk,
                  int64_t q_stride_b, int64_t q_stride_t, int64_t kv_stride_b, int64_t kv_stride_t, int64_t o_stride_b,
                  int64_t o_stride_t, int32_t dtype, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_attention"));
   KW_REQUIRE(q && k && v && out, "kw_attention: null pointer");
   if (dtype == KW_BF16 && g_gemm_impl.load() != 1) {
     int rc = attention_tc(q, k, v, out, B, H, Tq, Tk, q_stride_b, q_stride_t, kv_stride_b, kv_stride_t, o_stride_b,
@@ -625,6 +654,7 @@ int kw_attention(const void* q, const void* k, const void* v, void* out, int32_t
 
 int kw_linear(const void* A, const void* W, const float* bias, void* out, int32_t M, int32_t N, int32_t K, int32_t epi,
               int32_t a_dtype, int32_t w_dtype, int32_t out_dtype, int32_t impl, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_linear"));
   KW_REQUIRE(A && W && out && epi >= 0 && epi <= 2, "kw_linear: bad arguments");
   GemmArgs g = mk(A, K, (kw_dtype)a_dtype, W, (kw_dtype)w_dtype, bias, out, N, (kw_dtype)out_dtype, M, N, K, epi);
   if (impl == 1) return gemm_simt(g, (cudaStream_t)stream);
@@ -634,6 +664,7 @@ int kw_linear(const void* A, const void* W, const float* bias, void* out, int32_
 
 int kw_layernorm(const float* x, const float* w, const float* b, void* out, int32_t rows, int32_t d, int32_t out_dtype,
                  kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_layernorm"));
   KW_REQUIRE(x && w && b && out, "kw_layernorm: null pointer");
   return layernorm(x, w, b, out, rows, d, (kw_dtype)out_dtype, (cudaStream_t)stream);
 }

@@ -129,15 +129,15 @@ enum Epilogue {
 
 // Arguments of the fused vocabulary-projection epilogue (EPI_ARGMAX) and of its combine kernel.  Vocabulary rows below
 // tail0 (a multiple of 32, <= the first timestamp id: text ids only) are reduced inside the GEMM to one (best value, id)
-// pair per batch row and 32-row slice; rows >= tail0 (the ~1.5 k timestamp ids and the specials next to them) leave it as
+// pair per batch row and 64-row half tile; rows >= tail0 (the ~1.5 k timestamp ids and the specials next to them) leave it as
 // raw fp32 logits, because their rules need the whole timestamp range at once.
 struct SampleFuse {
   const int* tokens;           // [B, ld_tokens] token history (columns <= pos are read)
   int ld_tokens, pos, begin_index, return_ts;
   const unsigned char* flags;  // [vocab] bit0 = suppress, bit1 = suppress at begin
   SampleRules rules;
-  float2* vpart;               // [B][n_part] (best masked logit, its id as int bits) per 32-row text slice
-  int n_part;                  // tail0 / 32
+  float2* vpart;               // [B][n_part] (best masked logit, its id as int bits) per 64-row half tile of text ids
+  int n_part;                  // 2 * ceil(tail0 / 128)
   float* tail;                 // [B][tail_ld] raw logits of vocabulary rows tail0 .. vocab - 1
   int tail0, tail_ld;
 };

@@ -466,7 +466,9 @@ template <int R> struct Cfg {
   static constexpr int GROUP = R == 32 ? 4 : 2;  // (STAGES is a multiple of GROUP)
   static constexpr int RING = STAGES * STAGE_BYTES + (BM - R) * BK * 2;  // + tail the M = 128 read of the last stage may touch
   static constexpr int SLOTS = R == 32 ? MAX_SPLIT : 1;                  // split-K partial slots (R = 32 only)
-  static constexpr int OUT_STAGE = SLOTS * BN * R * 4;                   // [slot][batch row][feature] fp32
+  // [slot][batch row][feature] fp32; R = 128 (vocabulary): + one float of pitch per row and 768 B of rule tables for the
+  // fused arg-max epilogue (EPI_ARGMAX)
+  static constexpr int OUT_STAGE = SLOTS * BN * R * 4 + (R == 128 ? BN * 4 + 768 : 0);
   static constexpr size_t SMEM_BYTES = 1024 + (size_t)RING + 512 + OUT_STAGE;
 };
 static_assert(Cfg<32>::SMEM_BYTES <= 232448 && Cfg<40>::SMEM_BYTES <= 232448 && Cfg<128>::SMEM_BYTES <= 232448,
@@ -666,6 +668,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         }
         umma_commit(tfull_bar(as));
         stamp(4);
+        if (tcount == 0) stamp(11);
       }
     }
   } else {
@@ -675,15 +678,22 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     // slot `rank` of the staging buffer of the cluster's CTA 0 (this CTA's own buffer when there is no split)
     const uint32_t my_slot = out_stage_u32 + (uint32_t)rank * (BN * R * 4);
     const uint32_t slot_remote = S > 1 ? mapa_u32(my_slot, 0) : 0u;
-    // EPI_ARGMAX: per-row state of the timestamp rules, derived once per CTA from the token history
-    int* s_st = reinterpret_cast<int*>(out_stage);
-    int* s_bound = s_st + BN;
+    // EPI_ARGMAX: what the rules need to know about a batch row to mask TEXT ids (sr::text_col_mask), once per CTA from
+    // the last two tokens of the history.  Layout of the staging area: [64 column masks][128 lane bits][64 x 129 floats].
+    int* s_cm = reinterpret_cast<int*>(out_stage);
+    int* s_lb = s_cm + BN;
+    float* s_tile = reinterpret_cast<float*>(s_lb + 128);
+    constexpr int TP = 129;  // pitch of a batch row in s_tile: conflict-free both for the transposing writes and the scans
     if (R == 128 && p.epi == EPI_ARGMAX) {
-      for (int b = warp; b < p.M; b += SK_EPI_WARPS) {  // one warp per batch row, 32 history positions per step
-        int st, bd;
-        sr::row_state_warp(p.sf.tokens + (size_t)b * p.sf.ld_tokens, p.sf.pos, p.sf.begin_index, p.sf.rules.ts_begin,
-                           p.sf.return_ts, lane, &st, &bd);
-        if (lane == 0) { s_st[b] = st; s_bound[b] = bd; }
+      if (tid < BN) {
+        int cm = 0xf;  // rows past the batch: everything masked
+        if (tid < p.M) {
+          const int* trow = p.sf.tokens + (size_t)tid * p.sf.ld_tokens;
+          const int n = p.sf.pos + 1 - p.sf.begin_index;
+          const int t0 = n >= 1 ? trow[p.sf.pos] : 0, t1 = n >= 2 ? trow[p.sf.pos - 1] : 0;
+          cm = sr::text_col_mask(p.sf.return_ts, n, t0, t1, p.sf.rules.ts_begin);
+        }
+        s_cm[tid] = cm;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -691,62 +701,60 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       const int t = worker + tcount * n_workers;
       const uint32_t as = tcount & 1;
       if (R == 128 && p.epi == EPI_ARGMAX) {
-        // Fused logits processors + arg-max: lane = vocabulary row of this warp's 32-row slice, column = batch row.  A
-        // slice of text ids (all but the last ~48) is masked in place and reduced to ONE (best value, id) pair per batch
-        // row; the few slices that reach into the timestamp ids leave the kernel as raw fp32 logits (1.5 k per row) —
-        // their rules (pairing, monotonicity, logsumexp-vs-max) need the whole timestamp range and run in
-        // sample_combine_kernel.  The 13 MB fp32 logit matrix is never written.
-        mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
-        tc_fence_after();
+        // Fused logits processors + arg-max.  The accumulator (lane = vocabulary row, column = batch row) is transposed
+        // through shared memory; then thread (batch row, half tile) scans its 64 logits sequentially — masking is one AND
+        // of the id's lane bits with the row's column bits, ties keep the smaller id as torch.argmax does, and no
+        // warp-collective sits on the path (a cross-lane reduction per batch column cost ~8 us per tile).  Each thread
+        // emits ONE (best value, id) pair; the few 32-row slices that reach into the timestamp ids additionally leave
+        // the kernel as raw fp32 logits (1.5 k per row) — their rules (pairing, monotonicity, logsumexp-vs-max) need the
+        // whole timestamp range and run in sample_combine_kernel.  The 13 MB fp32 logit matrix is never written.
         const int lo = t * BM + warp * 32, v = lo + lane;
-        const bool valid = v < p.N;
-        const bool tail = lo >= p.sf.tail0;
-        const unsigned f = (valid && !tail) ? p.sf.flags[v] : 1u;
+        const bool valid = v < p.N, tail = lo >= p.sf.tail0;
+        // this lane's id against the row-independent half of the rules (sr::text_lane_bits); 0xf = masked for every row
+        s_lb[warp * 32 + lane] = (valid && !tail) ? (int)sr::text_lane_bits(p.sf.rules, p.sf.return_ts, v, p.sf.flags[v]) : 0xf;
+        mbar_wait(tfull_bar(as), (tcount >> 1) & 1);
+        if (threadIdx.x == 0 && tcount == 0) stamp(8);
+        tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + as * BN;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           if (c * 32 >= p.M) break;
           uint32_t r[32];
           tmem_ld32(taddr + c * 32, r);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (lo >= p.N) continue;  // slice past the end of the vocabulary (last tile)
-          if (tail) {
-            float* o = p.sf.tail + (size_t)(c * 32) * p.sf.tail_ld + (lo - p.sf.tail0) + lane;
+          if (tail && valid) {
+            float* o = p.sf.tail + (size_t)(c * 32) * p.sf.tail_ld + (v - p.sf.tail0);
+            const int nb = min(32, p.M - c * 32);
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (valid && c * 32 + j < p.M) o[(size_t)j * p.sf.tail_ld] = __uint_as_float(r[j]);
-            continue;
-          }
-          // mask, then a transposing butterfly — 16 + 8 + 4 + 2 + 1 exchanges instead of 32 x 5 — leaves column j's best
-          // in lane j
-          float xv[32];
-          int xi[32];
+              if (j < nb) o[(size_t)j * p.sf.tail_ld] = __uint_as_float(r[j]);
+          } else if (!tail) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int b = min(c * 32 + j, p.M - 1);
-            const bool ok = valid && !sr::token_masked(p.sf.rules, p.sf.return_ts, v, f, s_st[b], s_bound[b]);
-            xv[j] = ok ? __uint_as_float(r[j]) : -INFINITY;
-            xi[j] = ok ? v : p.N;
+            for (int j = 0; j < 32; ++j) s_tile[(c * 32 + j) * TP + warp * 32 + lane] = __uint_as_float(r[j]);
           }
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) {
-            const bool up = lane & o;
-#pragma unroll
-            for (int j = 0; j < o; ++j) {
-              const float sv = up ? xv[j] : xv[j + o], kv = up ? xv[j + o] : xv[j];
-              const int si = up ? xi[j] : xi[j + o], ki = up ? xi[j + o] : xi[j];
-              sr::Best rcv = {__shfl_xor_sync(0xffffffffu, sv, o), __shfl_xor_sync(0xffffffffu, si, o)};
-              sr::Best kp = {kv, ki};
-              kp = sr::better(kp, rcv);
-              xv[j] = kp.v;
-              xi[j] = kp.i;
-            }
-          }
-          const int b = c * 32 + lane;
-          if (b < p.M) p.sf.vpart[(size_t)b * p.sf.n_part + (lo >> 5)] = make_float2(xv[0], __int_as_float(xi[0]));
         }
         tc_fence_before();
         mbar_arrive(tempty_bar(as));
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // tile + lane bits staged
+        if (t * BM < p.sf.tail0) {                      // tiles that hold text ids emit partials
+          const int b = tid & (BN - 1), half = tid >> 6, cm = s_cm[b];
+          const float* row = s_tile + b * TP + half * 64;
+          const int* lbs = s_lb + half * 64;
+          float best = -INFINITY;
+          int bi = -1;
+#pragma unroll 16
+          for (int k = 0; k < 64; ++k) {
+            const float x = row[k];
+            const bool take = !(lbs[k] & cm) && x > best;  // strict: the first (smallest) id wins a tie
+            best = take ? x : best;
+            bi = take ? k : bi;
+          }
+          if (b < p.M)
+            p.sf.vpart[(size_t)b * p.sf.n_part + t * 2 + half] =
+                make_float2(best, __int_as_float(bi >= 0 ? t * BM + half * 64 + bi : p.N));
+        }
+        if (tcount + 1 < my_tiles) asm volatile("bar.sync 1, 128;" ::: "memory");  // staging free for the next tile
+        if (threadIdx.x == 0) stamp(tcount == 0 ? 9 : (tcount + 1 < my_tiles ? 5 : 6));
         continue;
       }
       // EPI_RESID: this thread's residual groups are requested before the accumulator wait (R = 32: 4 x 16 bytes)
@@ -870,7 +878,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   memset(&p.sf, 0, sizeof(p.sf));
   if (g.epi == EPI_ARGMAX) {
     if (!g.sample || !(g.M <= sk::BN) || g.N <= 8192) return KW_ERR_UNSUPPORTED;  // R = 128 decode-time kernel only
-    if (g.sample->tail0 % 32 != 0 || g.sample->n_part != g.sample->tail0 / 32 || g.sample->tail0 > g.N ||
+    if (g.sample->tail0 % 32 != 0 || g.sample->n_part != 2 * ceil_div(g.sample->tail0, 128) || g.sample->tail0 > g.N ||
         g.sample->tail_ld < g.N - g.sample->tail0)
       return KW_ERR_ARG;
     p.sf = *g.sample;

@@ -30,7 +30,7 @@ struct kw_model {
   void* self_v = nullptr;
   void* xkv = nullptr;  // [L][B*S][2d]
   int* finished = nullptr;
-  float* vpart = nullptr;  // [max_batch][tail0 / 32] float2 arg-max partials of the text slices (EPI_ARGMAX)
+  float* vpart = nullptr;  // [max_batch][2 * text tiles] float2 arg-max partials, one per 64-row half tile of text ids (EPI_ARGMAX)
   int* finished_host = nullptr;  // pinned
   cudaEvent_t finished_copied = nullptr;
   int enc_B = 0;

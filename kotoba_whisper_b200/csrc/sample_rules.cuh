@@ -90,7 +90,20 @@ __device__ __forceinline__ bool token_masked(const SampleRules& r, int return_ts
   return false;
 }
 
-constexpr int VP_WORDS = 5;  // partial: best text (value, id), best timestamp (value, id), sum exp(ts - best ts)
+// token_masked() for TEXT ids (v < ts_begin) factored into a row-independent half (lane bits: what the id is) and an
+// id-independent half (column bits: what the row's history says); the id is masked iff the two share a bit.
+//   bit0: suppressed always (suppress_tokens, or <|notimestamps|> under the timestamp rules)
+//   bit1: in begin_suppress_tokens            x   row is at its first sampled position
+//   bit2: id < eos                            x   timestamp rules: last token is a timestamp that opened a segment
+//   bit3: any text id                         x   timestamp rules: first sampled position (must be a timestamp)
+__device__ __forceinline__ unsigned text_lane_bits(const SampleRules& r, int return_ts, int v, unsigned f) {
+  return ((f & 1) || (return_ts && v == r.no_ts) ? 1u : 0u) | ((f & 2) ? 2u : 0u) | (v < r.eos ? 4u : 0u) | 8u;
+}
+// n = tokens sampled so far in this pass, t0 / t1 = last / second-to-last token of the history
+__device__ __forceinline__ int text_col_mask(int return_ts, int n, int t0, int t1, int tb) {
+  const bool at_begin = n == 0, last_ts = n >= 1 && t0 >= tb, pen_ts = n < 2 || t1 >= tb;
+  return 1 | (at_begin ? 2 : 0) | ((return_ts && last_ts && !pen_ts) ? 4 : 0) | ((return_ts && at_begin) ? 8 : 0);
+}
 
 }  // namespace sr
 }  // namespace kw
