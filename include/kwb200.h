@@ -243,6 +243,12 @@ void kw_set_decode_impl(int32_t impl);
  * the [B, vocab] fp32 logits are never written or re-read.  0: projection -> fp32 logits -> sample kernel.  Process-wide;
  * initial value from KW_SAMPLE_FUSED. */
 void kw_set_sample_fused(int32_t on);
+/* 1 (default): kw_greedy_pass replays the decoder positions as CUDA graphs — the kernel-per-op schedule of 8 consecutive
+ * positions captured once per (batch, prompt length, max_length, timestamps) and re-launched on later passes, tokens kept
+ * in a library-owned buffer and copied to the caller's at the end; the all-rows-finished poll runs between graphs.
+ * 0: every kernel launched from the host each pass.  Same kernels, same tokens.  Process-wide; initial value from
+ * KW_DECODE_GRAPH. */
+void kw_set_decode_graph(int32_t on);
 /* counts kernels launched by this library since the last reset (bench.py's gpu_launches) */
 int64_t kw_launch_count(int32_t reset);
 

@@ -68,6 +68,7 @@ SIGNATURES = {
     "kw_set_gemm_2cta": (None, [i32]),
     "kw_set_decode_impl": (None, [i32]),
     "kw_set_sample_fused": (None, [i32]),
+    "kw_set_decode_graph": (None, [i32]),
     "kw_debug_attention_desc": (None, [i32, i32, i32]),
     "kw_debug_gemm_stamps": (None, [vp]),
     "kw_profile_enable": (None, [C.c_uint32]),

@@ -70,6 +70,12 @@ static std::atomic<int> g_sample_fused{[] {
   return e ? atoi(e) : 1;
 }()};
 
+// 1 (default): kw_greedy_pass replays captured CUDA graphs of the decoder positions (KW_DECODE_GRAPH=0: eager launches)
+static std::atomic<int> g_decode_graph{[] {
+  const char* e = getenv("KW_DECODE_GRAPH");
+  return e ? atoi(e) : 1;
+}()};
+
 int gemm(const GemmArgs& g, cudaStream_t st) {
   const int impl = g_gemm_impl.load();
   if (impl != 1 && g.a_type == KW_BF16 && g.w_type == KW_BF16) {
@@ -92,8 +98,8 @@ static std::atomic<int> g_bound_device{-1};
 static int bound_device_ok(const char* who) {
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) {
-    set_error("%s: no CUDA device (this library has no CPU fallback)", who);
-    return KW_ERR_CUDA;
+    (void)cudaGetLastError();
+    return KW_OK;  // no device at all: argument checks first, the first CUDA call then fails loudly (no CPU fallback)
   }
   int expect = -1;
   if (g_bound_device.compare_exchange_strong(expect, dev) || expect == dev) return KW_OK;
@@ -166,6 +172,7 @@ void kw_set_gemm_impl(int32_t impl) { g_gemm_impl.store(impl); }
 void kw_set_gemm_2cta(int32_t on) { gemm_tc_set_2cta(on); }
 void kw_set_decode_impl(int32_t impl) { g_decode_impl.store(impl); }
 void kw_set_sample_fused(int32_t on) { g_sample_fused.store(on); }
+void kw_set_decode_graph(int32_t on) { g_decode_graph.store(on); }
 
 void kw_debug_attention_desc(int32_t v_lbo_bytes, int32_t v_sbo_bytes, int32_t v_kstep_bytes) {
   attention_tc_debug(v_lbo_bytes, v_sbo_bytes, v_kstep_bytes);
@@ -268,8 +275,9 @@ int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_ru
   const size_t szSelf = al(L * B * d * cfg->max_target_pos * es), szXkv = al(L * B * S * 2 * d * es);
   const size_t szDec = al(B * d * 4), szDqkv = al(B * 3 * d * 4), szDh = al(B * F * 4), szLog = al(B * (V + 32) * 4);
   const size_t szVp = al(B * (V / 32 + 1) * sizeof(float2));  // arg-max partials of the fused vocabulary epilogue
+  const size_t szTok = al(B * cfg->max_target_pos * sizeof(int));
   const size_t total = szP + szQ + 3 * szA + szX + 2 * szSelf + szXkv + 4 * szDec + szDqkv + szDh + szLog + al(V) +
-                       al(B * 4) + szVp;
+                       al(B * 4) + szVp + szTok;
   cudaError_t e = cudaMalloc(&m->pool, total);
   if (e != cudaSuccess) {
     set_error("kw_model_create: cudaMalloc(%zu bytes) failed: %s", total, cudaGetErrorString(e));
@@ -288,6 +296,7 @@ int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_ru
   m->flags = (unsigned char*)take(al(V));
   m->finished = (int*)take(al(B * 4));
   m->vpart = (float*)take(szVp);
+  m->gtokens = (int*)take(szTok);
 
   std::vector<unsigned char> hf(V, 0);
   for (int i = 0; i < rules->n_suppress; ++i) {
@@ -312,6 +321,8 @@ int kw_model_create(const kw_config* cfg, const kw_weights* w, const kw_token_ru
 void kw_model_destroy(kw_model* m) {
   if (!m) return;
   fused_decode_destroy(m);
+  for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   cudaFree(m->pool);
   if (m->finished_host) cudaFreeHost(m->finished_host);
   if (m->finished_copied) cudaEventDestroy(m->finished_copied);
@@ -412,24 +423,33 @@ static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int 
   const int d = c.d_model, S = c.max_source_pos, F = c.ffn_dim, H = c.n_heads, MT = c.max_target_pos;
   const size_t self_stride = (size_t)c.max_batch * d * MT * esize(t);
   const size_t xkv_stride = (size_t)c.max_batch * S * 2 * d * esize(t);
-  if (!pre_embedded) KW_TRY(embed(tokens, ld_tokens, pos, m->w.tok_embed, m->w.dec_pos, m->dx, B, d, c.vocab_size, t, st));
+  // bring-up / attribution only (KW_DECODE_SKIP, bit set of kernel kinds to leave out of the chain; results are garbage,
+  // the time difference is that kind's cost inside the dependent chain): 1 LayerNorm, 2 qkv, 4 self-attention, 8 out,
+  // 16 cross-q, 32 cross-attention, 64 cross-out, 128 fc1, 256 fc2, 1024 embedding  (512 = vocabulary + sampling, below)
+  static const int skip = getenv("KW_DECODE_SKIP") ? atoi(getenv("KW_DECODE_SKIP")) : 0;
+  if (!pre_embedded && !(skip & 1024)) KW_TRY(embed(tokens, ld_tokens, pos, m->w.tok_embed, m->w.dec_pos, m->dx, B, d, c.vocab_size, t, st));
   for (int l = 0; l < c.dec_layers; ++l) {
     const kw_dec_layer_weights& w = m->dec[l];
-    if (!(pre_embedded && l == 0)) KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, t, st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
-    KW_TRY(dec_self_attn(m->dqkv, (char*)m->self_k + l * self_stride, (char*)m->self_v + l * self_stride, m->dattn, B, d,
-                         H, MT, pos, t, st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, t, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
-    KW_TRY(layernorm(m->dx, w.lnx_w, w.lnx_b, m->da, B, d, t, st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), st));
-    {
+    if (!(pre_embedded && l == 0) && !(skip & 1)) KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, t, st));
+    if (!(skip & 2))
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
+    if (!(skip & 4))
+      KW_TRY(dec_self_attn(m->dqkv, (char*)m->self_k + l * self_stride, (char*)m->self_v + l * self_stride, m->dattn, B, d,
+                           H, MT, pos, t, st));
+    if (!(skip & 8))
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, t, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+    if (!(skip & 1)) KW_TRY(layernorm(m->dx, w.lnx_w, w.lnx_b, m->da, B, d, t, st));
+    if (!(skip & 16))
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), st));
+    if (!(skip & 32)) {
       ProfScope ps(KW_PROF_DEC_CROSS, (double)B * S * 2 * d * esize(t), st);  // algorithmic bytes: K and V read once
       KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st));
     }
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, t, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
-    KW_TRY(layernorm(m->dx, w.ln3_w, w.ln3_b, m->da, B, d, t, st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.w1, t, w.b1, m->dh, F, t, B, F, d, EPI_GELU), st));
-    KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dh, F, t, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), st));
+    if (!(skip & 64))
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, t, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+    if (!(skip & 1)) KW_TRY(layernorm(m->dx, w.ln3_w, w.ln3_b, m->da, B, d, t, st));
+    if (!(skip & 128)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.w1, t, w.b1, m->dh, F, t, B, F, d, EPI_GELU), st));
+    if (!(skip & 256)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dh, F, t, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), st));
   }
   return KW_OK;
 }
@@ -444,6 +464,8 @@ static int decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t 
   if (did_next) *did_next = false;
   KW_TRY(decode_hidden(m, tokens, ld_tokens, B, pos, st, pre_embedded));
   if (!sample && !logits_out) return KW_OK;
+  static const int skip = getenv("KW_DECODE_SKIP") ? atoi(getenv("KW_DECODE_SKIP")) : 0;
+  if (skip & 512) return KW_OK;
   KW_TRY(layernorm(m->dx, m->w.dec_ln_w, m->w.dec_ln_b, m->da, B, c.d_model, m->t, st));
   float* lg = logits_out ? logits_out : m->logits;
   if (sample && !logits_out && m->t == KW_BF16 && g_sample_fused.load() && g_gemm_impl.load() != 1) {
@@ -558,6 +580,95 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
     for (int pos = 0; pos < done; ++pos) pass_bytes += position_bytes(pos);
     if (g_prof.mask & (1u << KW_PROF_DEC_PASS)) g_prof.work[KW_PROF_DEC_PASS] += pass_bytes;
     return done;
+  }
+  // CUDA-graph replay: the kernel-per-op schedule of GRAPH_POS consecutive positions is captured once (on a private
+  // stream — the caller's may be the legacy default stream, which cannot capture) and re-launched on every later pass
+  // with the same shape; programmatic-launch edges are kept by the capture.  Not used while per-kernel profiling events
+  // or the in-kernel timeline stamps are active (they would be baked into the graph).
+  constexpr int GRAPH_POS = 8;
+  const unsigned per_kernel_prof = (1u << KW_PROF_DEC_GEMM) | (1u << KW_PROF_DEC_CROSS);
+  if (g_decode_graph.load() && !(g_prof.mask & per_kernel_prof) && !getenv("KW_DECODE_SKIP")) {
+    const int cfg_epoch = g_sample_fused.load() | (g_gemm_impl.load() << 1);
+    if (!m->cap_stream) KW_CUDA_OK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+    int* gt = m->gtokens;
+    fill_prompt_kernel<<<ceil_div(B, 128), 128, 0, st>>>(gt, max_length, B, p0, n_prompt, m->rules.pad, m->finished);
+    KW_LAUNCH_OK();
+    ++g_launches;
+    bool pre = false, stop = false;
+    int pos = 0;
+    while (pos + 1 < max_length && !stop) {
+      const int end = std::min(pos + GRAPH_POS, max_length - 1);
+      kw_model::PassGraph* pg = nullptr;
+      for (auto& g : m->graphs)
+        if (g.B == B && g.n_prompt == n_prompt && g.max_length == max_length && g.return_ts == return_timestamps &&
+            g.pos0 == pos && g.pos1 == end && g.pre_in == (int)pre && g.cfg_epoch == cfg_epoch) {
+          pg = &g;
+          break;
+        }
+      if (!pg) {
+        if (m->graphs.size() >= 512) {  // shapes keep changing (ragged last batches): start over instead of growing
+          for (auto& g : m->graphs) cudaGraphExecDestroy(g.exec);
+          m->graphs.clear();
+        }
+        kw_model::PassGraph ng = {B, n_prompt, max_length, return_timestamps, pos, end, (int)pre, cfg_epoch, nullptr, 0, false};
+        const long long l0 = g_launches.load();
+        KW_CUDA_OK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+        int rc = KW_OK;
+        bool pr = pre;
+        for (int q = pos; q < end && rc == KW_OK; ++q) {
+          bool did = false;
+          rc = decode_step(m, gt, max_length, B, q, n_prompt, q >= n_prompt - 1, return_timestamps, m->finished, nullptr,
+                           m->cap_stream, pr, q + 2 < max_length, &did);
+          pr = did;
+        }
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &graph);
+        ng.n_launch = (int)(g_launches.load() - l0);
+        g_launches.store(l0);
+        if (rc != KW_OK) {
+          if (graph) cudaGraphDestroy(graph);
+          return rc;
+        }
+        if (ce != cudaSuccess || !graph) {
+          set_error("kw_greedy_pass: graph capture failed: %s", cudaGetErrorString(ce));
+          return KW_ERR_CUDA;
+        }
+        ce = cudaGraphInstantiate(&ng.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+          set_error("kw_greedy_pass: graph instantiation failed: %s", cudaGetErrorString(ce));
+          return KW_ERR_CUDA;
+        }
+        ng.pre_out = pr;
+        m->graphs.push_back(ng);
+        pg = &m->graphs.back();
+      }
+      KW_CUDA_OK(cudaGraphLaunch(pg->exec, st));
+      g_launches += pg->n_launch;
+      pre = pg->pre_out;
+      for (int q = pos; q < end; ++q) pass_bytes += position_bytes(q);
+      steps += end - pos;
+      pos = end;
+      // all-rows-finished poll with one graph of lag: the flags copied out behind graph i are looked at after graph
+      // i + 1 has been enqueued, so the GPU never waits for the host
+      if (check_every > 0 && pos + 1 < max_length) {
+        if (pending_since >= 0) {
+          KW_CUDA_OK(cudaEventSynchronize(m->finished_copied));
+          bool all = true;
+          for (int b = 0; b < B; ++b) all = all && m->finished_host[b];
+          stop = all;
+        }
+        if (!stop && pos >= n_prompt) {
+          KW_CUDA_OK(cudaMemcpyAsync(m->finished_host, m->finished, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+          KW_CUDA_OK(cudaEventRecord(m->finished_copied, st));
+          pending_since = pos;
+        }
+      }
+    }
+    if (pending_since >= 0) KW_CUDA_OK(cudaEventSynchronize(m->finished_copied));
+    KW_CUDA_OK(cudaMemcpyAsync(tokens, gt, (size_t)B * max_length * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (g_prof.mask & (1u << KW_PROF_DEC_PASS)) g_prof.work[KW_PROF_DEC_PASS] += pass_bytes;
+    return steps;
   }
   bool pre_embedded = false;
   for (int pos = 0; pos + 1 < max_length; ++pos) {

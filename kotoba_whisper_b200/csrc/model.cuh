@@ -34,6 +34,16 @@ struct kw_model {
   int* finished_host = nullptr;  // pinned
   cudaEvent_t finished_copied = nullptr;
   int enc_B = 0;
+  // CUDA-graph replay of the decoder positions (api.cu kw_greedy_pass): captured chunks, capture stream, token buffer
+  struct PassGraph {
+    int B, n_prompt, max_length, return_ts, pos0, pos1, pre_in, cfg_epoch;
+    cudaGraphExec_t exec;
+    int n_launch;
+    bool pre_out;
+  };
+  std::vector<PassGraph> graphs;
+  cudaStream_t cap_stream = nullptr;
+  int* gtokens = nullptr;  // [max_batch, max_target_pos] tokens of the pass being decoded (graphs bake this pointer)
   kw::FusedDecode* fused = nullptr;  // persistent decode kernel state (bf16 models), built lazily
 };
 

@@ -8,6 +8,7 @@ from bench import KOTOBA, synth_audio  # noqa: E402
 from kotoba_whisper_b200 import WhisperB200Config, WhisperB200ForConditionalGeneration, WhisperFeatureExtractorB200, _lib  # noqa: E402
 from kotoba_whisper_b200.random_init import random_state_dict  # noqa: E402
 lib = _lib.load()
+lib.kw_set_decode_graph(0)  # the stamp pointer must not be baked into a captured graph
 B = 64
 dev = torch.device("cuda", 0)
 cfg = WhisperB200Config(**dict(KOTOBA, encoder_layers=2))
