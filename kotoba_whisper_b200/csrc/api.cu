@@ -47,7 +47,8 @@ void gemm_tc_set_stamps(unsigned long long* p);
 void gemm_tc_set_2cta(int on);
 int dec_self_attn(const float* qkv, void* kc, void* vc, void* out, int B, int d, int H, int max_t, int pos, kw_dtype t,
                   cudaStream_t st);
-int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int H, int S, kw_dtype t, cudaStream_t st);
+int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int H, int S, kw_dtype t, cudaStream_t st,
+                   int hint, int head_rows);
 int sample_launch(const float* logits, const unsigned char* flags, const SampleRules& r, int* tokens, int ld_tokens,
                   int B, int pos, int begin_index, int return_ts, int* finished, cudaStream_t st);
 
@@ -428,28 +429,58 @@ static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int 
   // 16 cross-q, 32 cross-attention, 64 cross-out, 128 fc1, 256 fc2, 1024 embedding  (512 = vocabulary + sampling, below)
   static const int skip = getenv("KW_DECODE_SKIP") ? atoi(getenv("KW_DECODE_SKIP")) : 0;
   if (!pre_embedded && !(skip & 1024)) KW_TRY(embed(tokens, ld_tokens, pos, m->w.tok_embed, m->w.dec_pos, m->dx, B, d, c.vocab_size, t, st));
+  // L2 management of the decode step (process-wide knobs, read once):
+  //   KW_XA_HINT   eviction priority of the cross-attention K/V stream (0 none, 1 all evict_first, 2 head rows evict_last +
+  //                tail evict_first, 3 head rows normal + tail evict_first); KW_XA_ROWS = head rows per utterance
+  //   KW_L2PF_MASK which projections pull the head rows of the NEXT cross-attention into L2 while they run (bit 0 qkv,
+  //                1 out, 2 cross-q: same layer; 3 cross-out, 4 fc1, 5 fc2: next layer / next position's layer 0)
+  //   KW_W_HINT    eviction priority of the decoder-layer weight loads (0 normal, 1 evict_last, 2 evict_first)
+  static const int xa_hint = getenv("KW_XA_HINT") ? atoi(getenv("KW_XA_HINT")) : 0;
+  static const int xa_rows = getenv("KW_XA_ROWS") ? atoi(getenv("KW_XA_ROWS")) : 0;
+  static const int pf_mask = getenv("KW_L2PF_MASK") ? atoi(getenv("KW_L2PF_MASK")) : 0;
+  static const int w_hint = getenv("KW_W_HINT") ? atoi(getenv("KW_W_HINT")) : 0;
+  const int row_bytes = 2 * d * (int)esize(t);
+  const int n_pre = __builtin_popcount(pf_mask & 7), n_post = __builtin_popcount(pf_mask & 56);
+  auto with_l2 = [&](GemmArgs g, int bit, int l) {
+    g.w_hint = w_hint;
+    if (!(pf_mask & (1 << bit)) || xa_rows <= 0 || t != KW_BF16) return g;
+    // the head rows are split between the "pre" group (bits 0-2, this layer's cross-attention) and the "post" group
+    // (bits 3-5, the next cross-attention), each group's share divided evenly over its members
+    const bool post = bit >= 3;
+    const int groups = (n_pre ? 1 : 0) + (n_post ? 1 : 0);
+    const int rows_group = xa_rows / groups, r0_group = (post && n_pre) ? rows_group : 0;
+    const int members = post ? n_post : n_pre;
+    const int idx = __builtin_popcount(pf_mask & ((1 << bit) - 1) & (post ? 56 : 7));
+    const int rows = rows_group / members, r0 = r0_group + idx * rows;
+    const int tl = post ? (l + 1) % c.dec_layers : l;
+    g.l2pf_base = (const char*)m->xkv + tl * xkv_stride + (size_t)r0 * row_bytes;
+    g.l2pf_stride = (long long)S * row_bytes;
+    g.l2pf_len = rows * row_bytes;
+    g.l2pf_n = B;
+    return g;
+  };
   for (int l = 0; l < c.dec_layers; ++l) {
     const kw_dec_layer_weights& w = m->dec[l];
     if (!(pre_embedded && l == 0) && !(skip & 1)) KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, t, st));
     if (!(skip & 2))
-      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), st));
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), 0, l), st));
     if (!(skip & 4))
       KW_TRY(dec_self_attn(m->dqkv, (char*)m->self_k + l * self_stride, (char*)m->self_v + l * self_stride, m->dattn, B, d,
                            H, MT, pos, t, st));
     if (!(skip & 8))
-      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, t, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dattn, d, t, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), 1, l), st));
     if (!(skip & 1)) KW_TRY(layernorm(m->dx, w.lnx_w, w.lnx_b, m->da, B, d, t, st));
     if (!(skip & 16))
-      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), st));
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), 2, l), st));
     if (!(skip & 32)) {
       ProfScope ps(KW_PROF_DEC_CROSS, (double)B * S * 2 * d * esize(t), st);  // algorithmic bytes: K and V read once
-      KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st));
+      KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st, xa_hint, xa_rows));
     }
     if (!(skip & 64))
-      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dattn, d, t, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), st));
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dattn, d, t, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), 3, l), st));
     if (!(skip & 1)) KW_TRY(layernorm(m->dx, w.ln3_w, w.ln3_b, m->da, B, d, t, st));
-    if (!(skip & 128)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->da, d, t, w.w1, t, w.b1, m->dh, F, t, B, F, d, EPI_GELU), st));
-    if (!(skip & 256)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, mk(m->dh, F, t, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), st));
+    if (!(skip & 128)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.w1, t, w.b1, m->dh, F, t, B, F, d, EPI_GELU), 4, l), st));
+    if (!(skip & 256)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dh, F, t, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), 5, l), st));
   }
   return KW_OK;
 }
@@ -481,6 +512,8 @@ static int decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t 
     GemmArgs g = mk(m->da, c.d_model, m->t, m->w.tok_embed, m->t, nullptr, nullptr, c.vocab_size, KW_F32, B, c.vocab_size,
                     c.d_model, EPI_ARGMAX);
     g.sample = &sf;
+    static const int vocab_hint = getenv("KW_VOCAB_HINT") ? atoi(getenv("KW_VOCAB_HINT")) : 0;
+    g.w_hint = vocab_hint;  // 133 MB read once per position: 2 = evict_first keeps it from displacing the layer weights
     int rc;
     {
       ProfScope ps(KW_PROF_DEC_GEMM, gemm_flops(g), st);

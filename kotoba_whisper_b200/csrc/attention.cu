@@ -204,6 +204,10 @@ template <typename T> struct Raw8;
 template <> struct Raw8<bf16> {
   uint4 r;
   __device__ __forceinline__ void load(const bf16* p) { r = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void load_hint(const bf16* p, uint64_t pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+  }
   __device__ __forceinline__ void unpack(float* f) const {
     const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
@@ -219,6 +223,12 @@ template <> struct Raw8<float> {
   __device__ __forceinline__ void load(const float* p) {
     a = *reinterpret_cast<const float4*>(p);
     b = *reinterpret_cast<const float4*>(p + 4);
+  }
+  __device__ __forceinline__ void load_hint(const float* p, uint64_t pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p + 4), "l"(pol));
   }
   __device__ __forceinline__ void unpack(float* f) const {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
@@ -349,7 +359,15 @@ constexpr int XA_THREADS = 128, XA_WARPS = XA_THREADS / 32, XA_UNROLL = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(XA_THREADS, 10)
-dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T* __restrict__ out, int d, int S) {
+dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T* __restrict__ out, int d, int S,
+                      int hint, int head_rows) {
+  // L2 eviction priority of the K/V stream (hint != 0): rows >= head_rows are read once per position and are far larger
+  // than L2 -> evict_first, so they do not push out what is worth keeping (weights, the head rows).  Rows < head_rows:
+  // hint 2 = evict_last (they stay resident from one position to the next), hint 1 / 3 = normal priority.
+  const uint64_t pol_tail = l2_evict_first();
+  uint64_t pol_head;
+  if (hint == 2) pol_head = l2_evict_last();
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_head));
   // 128-thread CTAs: all B*H CTAs (1280 at B = 64) are resident at once (<= 16 per SM), so there is no partial second
   // wave; each warp keeps XA_UNROLL independent 16-byte loads per lane in flight.
   extern __shared__ float s_p[];  // [S]
@@ -373,7 +391,10 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T*
 #pragma unroll
     for (int u = 0; u < XA_UNROLL; ++u) {
       jj[u] = j0 + (u * XA_WARPS + warp) * 4 + sub;
-      if (jj[u] < S) kr[u].load(kbase + (size_t)jj[u] * ld);
+      if (jj[u] < S) {
+        if (hint) kr[u].load_hint(kbase + (size_t)jj[u] * ld, jj[u] < head_rows ? pol_head : pol_tail);
+        else kr[u].load(kbase + (size_t)jj[u] * ld);
+      }
     }
 #pragma unroll
     for (int u = 0; u < XA_UNROLL; ++u) {
@@ -423,7 +444,10 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T*
 #pragma unroll
     for (int u = 0; u < XA_UNROLL; ++u) {
       jj[u] = j0 + (u * XA_WARPS + warp) * 4 + sub;
-      if (jj[u] < S) vr[u].load(vbase + (size_t)jj[u] * ld);
+      if (jj[u] < S) {
+        if (hint) vr[u].load_hint(vbase + (size_t)jj[u] * ld, jj[u] < head_rows ? pol_head : pol_tail);
+        else vr[u].load(vbase + (size_t)jj[u] * ld);
+      }
     }
 #pragma unroll
     for (int u = 0; u < XA_UNROLL; ++u) {
@@ -455,13 +479,13 @@ dec_cross_attn_kernel(const float* __restrict__ q, const T* __restrict__ xkv, T*
 }
 
 int dec_cross_attn(const float* q, const void* xkv, void* out, int B, int d, int H, int S, kw_dtype t,
-                   cudaStream_t st) {
+                   cudaStream_t st, int hint, int head_rows) {
   dim3 grid(H, B);
   const size_t smem = sizeof(float) * S;
   if (t == KW_BF16)
-    KW_CUDA_OK(launch_pdl(PDL_CROSS_ATTN, dec_cross_attn_kernel<bf16>, grid, dim3(XA_THREADS), smem, st, q, (const bf16*)xkv, (bf16*)out, d, S));
+    KW_CUDA_OK(launch_pdl(PDL_CROSS_ATTN, dec_cross_attn_kernel<bf16>, grid, dim3(XA_THREADS), smem, st, q, (const bf16*)xkv, (bf16*)out, d, S, hint, head_rows));
   else
-    KW_CUDA_OK(launch_pdl(PDL_CROSS_ATTN, dec_cross_attn_kernel<float>, grid, dim3(XA_THREADS), smem, st, q, (const float*)xkv, (float*)out, d, S));
+    KW_CUDA_OK(launch_pdl(PDL_CROSS_ATTN, dec_cross_attn_kernel<float>, grid, dim3(XA_THREADS), smem, st, q, (const float*)xkv, (float*)out, d, S, hint, head_rows));
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

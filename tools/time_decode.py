@@ -25,9 +25,13 @@ for rep in range(N + 2):
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    model._greedy_pass(B, [50258, 50266, 50360, 50364], 128, False)
+    out = model._greedy_pass(B, [50258, 50266, 50360, 50364], 128, False)
     b.record()
     torch.cuda.synchronize()
     if rep >= 2:
         ts.append(a.elapsed_time(b))
+import numpy as np  # noqa: E402
+ids = np.asarray(out).astype(np.int64).ravel()
+chk = int((ids * (np.arange(1, ids.size + 1) % 1009)).sum())
+print(f"tokens checksum {chk}  ", end="")
 print(f"greedy pass B={B}: mean {sum(ts)/len(ts):.2f} ms  min {min(ts):.2f}  max {max(ts):.2f}  ({N} reps)")
