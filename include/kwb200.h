@@ -174,6 +174,17 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
 int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
                    int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream);
 
+/* Two batches in flight (throughput mode of the labelling loop, run_pseudo_labelling.py:333-341: `for batch in loader:
+ * generate(batch)`): the encoder of the NEXT batch (`enc`, features `mel` dev f32 [B_enc, n_mels, 2*max_source_pos]) runs
+ * in layer groups with the greedy pass of the PREVIOUS batch (`dec`, encoder output already in place; arguments as
+ * kw_greedy_pass) slotted between the groups on the same stream.  Same kernels and results as kw_encode(enc) followed
+ * by kw_greedy_pass(dec).  `enc` and `dec` must be two handles (kw_model_create twice over the same weight table: two
+ * workspaces, one copy of the weights).  dec == NULL: encoder only.  Returns the number of decoder positions evaluated
+ * (0 when dec == NULL) or a negative kw_status. */
+int kw_encode_decode(kw_model* enc, const float* mel, int32_t B_enc, kw_model* dec, int32_t B_dec, const int32_t* prompt,
+                     int32_t n_prompt, int32_t max_length, int32_t return_timestamps, int32_t check_every,
+                     int32_t* tokens, kw_stream stream);
+
 /* Teacher-forcing decoder forward (no KV cache) on the handle's current encoder output: all T positions at once,
  * causal self-attention, cross-attention over the encoder K/V, proj_out — what `teacher_model(encoder_outputs=...,
  * labels=...)` computes in the reference's distillation step (run_distillation.py:641-649; WhisperDecoder.forward,

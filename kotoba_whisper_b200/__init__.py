@@ -8,7 +8,7 @@ CPU or PyTorch fallback: a missing libkwb200.so or CUDA device raises.
 """
 from ._lib import KwError, LIB_PATH  # noqa: F401
 from .feature_extraction import BatchFeature, LogMelProducer, WhisperFeatureExtractorB200  # noqa: F401
-from .modeling import (WhisperB200Config, WhisperB200ForConditionalGeneration,  # noqa: F401
+from .modeling import (GenerateStream, WhisperB200Config, WhisperB200ForConditionalGeneration,  # noqa: F401
                        WhisperB200GenerationConfig)
 from .pipeline import AsrPipelineB200, chunk_iter, merge_chunk_tokens, transcribe_longform  # noqa: F401
 # the `pipeline(...)` factory lives in kotoba_whisper_b200.pipeline (not re-exported: it would shadow the submodule)

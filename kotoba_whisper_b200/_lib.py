@@ -58,6 +58,7 @@ SIGNATURES = {
     "kw_cross_kv": (i32, [vp, i32, vp]),
     "kw_decode_step": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "kw_greedy_pass": (i32, [vp, i32, C.POINTER(i32), i32, i32, i32, i32, vp, vp]),
+    "kw_encode_decode": (i32, [vp, vp, i32, vp, i32, C.POINTER(i32), i32, i32, i32, i32, vp, vp]),
     "kw_decoder_forward": (i32, [vp, vp, i32, i32, vp, vp]),
     "kw_attention": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, i64, i64, i64, i32, vp]),
     "kw_linear": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -347,25 +348,26 @@ static int gemm_p(int cat, const GemmArgs& g, cudaStream_t st) {
   return gemm(g, st);
 }
 
-int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_stream stream) {
-  KW_TRY(bound_device_ok("kw_encode"));
-  KW_REQUIRE(m && mel, "kw_encode: null argument");
-  KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch, "kw_encode: B=%d outside [1, max_batch=%d]", B, m->cfg.max_batch);
-  cudaStream_t st = (cudaStream_t)stream;
+// The encoder in three pieces so that kw_encode_decode can slot decoder positions of ANOTHER batch between layer groups.
+static int encode_stem(kw_model* m, const float* mel, int B, cudaStream_t st) {
   const kw_config& c = m->cfg;
   const kw_dtype t = m->t;
-  const int d = c.d_model, S = c.max_source_pos, T2 = 2 * S, F = c.ffn_dim, M = B * S;
+  const int d = c.d_model, S = c.max_source_pos, T2 = 2 * S, M = B * S;
   // conv stem as two im2col GEMMs (modeling_whisper.py:619-625)
   KW_TRY(im2col_conv1(mel, m->bufP, B, c.n_mels, T2, t, st));
   KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->bufP, 3 * c.n_mels, t, m->w.conv1_w, t, m->w.conv1_b, m->bufQ, d, t, B * T2, d, 3 * c.n_mels, EPI_GELU), st));
   KW_TRY(im2col_conv2(m->bufQ, m->bufP, B, d, T2, S, t, st));
-  {
-    GemmArgs g = mk(m->bufP, 3 * d, t, m->w.conv2_w, t, m->w.conv2_b, m->x, d, KW_F32, M, d, 3 * d, EPI_GELU_POS);
-    g.pos = m->w.enc_pos;
-    g.pos_period = S;
-    KW_TRY(gemm_p(KW_PROF_ENC_GEMM, g, st));
-  }
-  for (int l = 0; l < c.enc_layers; ++l) {
+  GemmArgs g = mk(m->bufP, 3 * d, t, m->w.conv2_w, t, m->w.conv2_b, m->x, d, KW_F32, M, d, 3 * d, EPI_GELU_POS);
+  g.pos = m->w.enc_pos;
+  g.pos_period = S;
+  return gemm_p(KW_PROF_ENC_GEMM, g, st);
+}
+
+static int encode_layers(kw_model* m, int B, int l0, int l1, cudaStream_t st) {
+  const kw_config& c = m->cfg;
+  const kw_dtype t = m->t;
+  const int d = c.d_model, S = c.max_source_pos, F = c.ffn_dim, M = B * S;
+  for (int l = l0; l < l1 && l < c.enc_layers; ++l) {
     const kw_enc_layer_weights& w = m->enc[l];
     KW_TRY(layernorm(m->x, w.ln1_w, w.ln1_b, m->a, M, d, t, st));
     KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->a, d, t, w.wqkv, t, w.bqkv, m->bufP, 3 * d, t, M, 3 * d, d, EPI_STORE), st));
@@ -387,10 +389,26 @@ int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_strea
     KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->a, d, t, w.w1, t, w.b1, m->bufQ, F, t, M, F, d, EPI_GELU), st));
     KW_TRY(gemm_p(KW_PROF_ENC_GEMM, mk(m->bufQ, F, t, w.w2, t, w.b2, m->x, d, KW_F32, M, d, F, EPI_RESID), st));
   }
-  KW_TRY(layernorm(m->x, m->w.enc_ln_w, m->w.enc_ln_b, m->enc_out, M, d, t, st));
+  return KW_OK;
+}
+
+static int encode_finish(kw_model* m, int B, float* enc_out, cudaStream_t st) {
+  const kw_config& c = m->cfg;
+  const int M = B * c.max_source_pos, d = c.d_model;
+  KW_TRY(layernorm(m->x, m->w.enc_ln_w, m->w.enc_ln_b, m->enc_out, M, d, m->t, st));
   if (enc_out) KW_TRY(layernorm(m->x, m->w.enc_ln_w, m->w.enc_ln_b, enc_out, M, d, KW_F32, st));
   m->enc_B = B;
   return KW_OK;
+}
+
+int kw_encode(kw_model* m, const float* mel, int32_t B, float* enc_out, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_encode"));
+  KW_REQUIRE(m && mel, "kw_encode: null argument");
+  KW_REQUIRE(B >= 1 && B <= m->cfg.max_batch, "kw_encode: B=%d outside [1, max_batch=%d]", B, m->cfg.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  KW_TRY(encode_stem(m, mel, B, st));
+  KW_TRY(encode_layers(m, B, 0, m->cfg.enc_layers, st));
+  return encode_finish(m, B, enc_out, st);
 }
 
 int kw_set_encoder_output(kw_model* m, const float* enc, int32_t B, kw_stream stream) {
@@ -429,58 +447,40 @@ static int decode_hidden(kw_model* m, const int32_t* tokens, int ld_tokens, int 
   // 16 cross-q, 32 cross-attention, 64 cross-out, 128 fc1, 256 fc2, 1024 embedding  (512 = vocabulary + sampling, below)
   static const int skip = getenv("KW_DECODE_SKIP") ? atoi(getenv("KW_DECODE_SKIP")) : 0;
   if (!pre_embedded && !(skip & 1024)) KW_TRY(embed(tokens, ld_tokens, pos, m->w.tok_embed, m->w.dec_pos, m->dx, B, d, c.vocab_size, t, st));
-  // L2 management of the decode step (process-wide knobs, read once):
-  //   KW_XA_HINT   eviction priority of the cross-attention K/V stream (0 none, 1 all evict_first, 2 head rows evict_last +
-  //                tail evict_first, 3 head rows normal + tail evict_first); KW_XA_ROWS = head rows per utterance
-  //   KW_L2PF_MASK which projections pull the head rows of the NEXT cross-attention into L2 while they run (bit 0 qkv,
-  //                1 out, 2 cross-q: same layer; 3 cross-out, 4 fc1, 5 fc2: next layer / next position's layer 0)
-  //   KW_W_HINT    eviction priority of the decoder-layer weight loads (0 normal, 1 evict_last, 2 evict_first)
-  static const int xa_hint = getenv("KW_XA_HINT") ? atoi(getenv("KW_XA_HINT")) : 0;
-  static const int xa_rows = getenv("KW_XA_ROWS") ? atoi(getenv("KW_XA_ROWS")) : 0;
-  static const int pf_mask = getenv("KW_L2PF_MASK") ? atoi(getenv("KW_L2PF_MASK")) : 0;
-  static const int w_hint = getenv("KW_W_HINT") ? atoi(getenv("KW_W_HINT")) : 0;
-  const int row_bytes = 2 * d * (int)esize(t);
-  const int n_pre = __builtin_popcount(pf_mask & 7), n_post = __builtin_popcount(pf_mask & 56);
-  auto with_l2 = [&](GemmArgs g, int bit, int l) {
+  // L2 eviction priorities of the decode step (measured on B200, greedy pass alone at B = 64, same box): cross-attention
+  // K/V stream evict_first + decoder-layer weights evict_last + vocabulary matrix evict_first 45.97 -> 45.46 ms.  Keeping
+  // a head of the K/V rows resident (evict_last on 64-192 rows per utterance: 45.9-46.1 ms) or pulling them into L2 from
+  // the projections that run before each cross-attention (cp.async.bulk.prefetch.L2, 63-94 MB per cross-attention:
+  // 46.3-47.0 ms) did not pay: the projections are latency-bound and slow down under the extra traffic by as much as
+  // the cross-attention gains.  KW_XA_HINT / KW_W_HINT = 0 turn the hints off.
+  static const int xa_hint = getenv("KW_XA_HINT") ? atoi(getenv("KW_XA_HINT")) : 1;
+  static const int w_hint = getenv("KW_W_HINT") ? atoi(getenv("KW_W_HINT")) : 1;
+  auto with_l2 = [&](GemmArgs g) {
     g.w_hint = w_hint;
-    if (!(pf_mask & (1 << bit)) || xa_rows <= 0 || t != KW_BF16) return g;
-    // the head rows are split between the "pre" group (bits 0-2, this layer's cross-attention) and the "post" group
-    // (bits 3-5, the next cross-attention), each group's share divided evenly over its members
-    const bool post = bit >= 3;
-    const int groups = (n_pre ? 1 : 0) + (n_post ? 1 : 0);
-    const int rows_group = xa_rows / groups, r0_group = (post && n_pre) ? rows_group : 0;
-    const int members = post ? n_post : n_pre;
-    const int idx = __builtin_popcount(pf_mask & ((1 << bit) - 1) & (post ? 56 : 7));
-    const int rows = rows_group / members, r0 = r0_group + idx * rows;
-    const int tl = post ? (l + 1) % c.dec_layers : l;
-    g.l2pf_base = (const char*)m->xkv + tl * xkv_stride + (size_t)r0 * row_bytes;
-    g.l2pf_stride = (long long)S * row_bytes;
-    g.l2pf_len = rows * row_bytes;
-    g.l2pf_n = B;
     return g;
   };
   for (int l = 0; l < c.dec_layers; ++l) {
     const kw_dec_layer_weights& w = m->dec[l];
     if (!(pre_embedded && l == 0) && !(skip & 1)) KW_TRY(layernorm(m->dx, w.ln1_w, w.ln1_b, m->da, B, d, t, st));
     if (!(skip & 2))
-      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE), 0, l), st));
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.wqkv, t, w.bqkv, m->dqkv, 3 * d, KW_F32, B, 3 * d, d, EPI_STORE)), st));
     if (!(skip & 4))
       KW_TRY(dec_self_attn(m->dqkv, (char*)m->self_k + l * self_stride, (char*)m->self_v + l * self_stride, m->dattn, B, d,
                            H, MT, pos, t, st));
     if (!(skip & 8))
-      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dattn, d, t, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID), 1, l), st));
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dattn, d, t, w.wo, t, w.bo, m->dx, d, KW_F32, B, d, d, EPI_RESID)), st));
     if (!(skip & 1)) KW_TRY(layernorm(m->dx, w.lnx_w, w.lnx_b, m->da, B, d, t, st));
     if (!(skip & 16))
-      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE), 2, l), st));
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.wq_x, t, w.bq_x, m->dq, d, KW_F32, B, d, d, EPI_STORE)), st));
     if (!(skip & 32)) {
       ProfScope ps(KW_PROF_DEC_CROSS, (double)B * S * 2 * d * esize(t), st);  // algorithmic bytes: K and V read once
-      KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st, xa_hint, xa_rows));
+      KW_TRY(dec_cross_attn(m->dq, (char*)m->xkv + l * xkv_stride, m->dattn, B, d, H, S, t, st, xa_hint, 0));
     }
     if (!(skip & 64))
-      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dattn, d, t, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID), 3, l), st));
+      KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dattn, d, t, w.wo_x, t, w.bo_x, m->dx, d, KW_F32, B, d, d, EPI_RESID)), st));
     if (!(skip & 1)) KW_TRY(layernorm(m->dx, w.ln3_w, w.ln3_b, m->da, B, d, t, st));
-    if (!(skip & 128)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.w1, t, w.b1, m->dh, F, t, B, F, d, EPI_GELU), 4, l), st));
-    if (!(skip & 256)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dh, F, t, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID), 5, l), st));
+    if (!(skip & 128)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->da, d, t, w.w1, t, w.b1, m->dh, F, t, B, F, d, EPI_GELU)), st));
+    if (!(skip & 256)) KW_TRY(gemm_p(KW_PROF_DEC_GEMM, with_l2(mk(m->dh, F, t, w.w2, t, w.b2, m->dx, d, KW_F32, B, d, F, EPI_RESID)), st));
   }
   return KW_OK;
 }
@@ -512,7 +512,7 @@ static int decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t 
     GemmArgs g = mk(m->da, c.d_model, m->t, m->w.tok_embed, m->t, nullptr, nullptr, c.vocab_size, KW_F32, B, c.vocab_size,
                     c.d_model, EPI_ARGMAX);
     g.sample = &sf;
-    static const int vocab_hint = getenv("KW_VOCAB_HINT") ? atoi(getenv("KW_VOCAB_HINT")) : 0;
+    static const int vocab_hint = getenv("KW_VOCAB_HINT") ? atoi(getenv("KW_VOCAB_HINT")) : 2;
     g.w_hint = vocab_hint;  // 133 MB read once per position: 2 = evict_first keeps it from displacing the layer weights
     int rc;
     {
@@ -568,8 +568,25 @@ __global__ void fill_prompt_kernel(int* tokens, int ld, int B, const int4 p0, in
   finished[b] = 0;
 }
 
+// `between`: called before every group of GRAPH_POS positions (kw_encode_decode slots encoder layers of another batch there)
+static int greedy_pass_impl(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
+                            int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream,
+                            const std::function<int()>* between);
+
 int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
                    int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream) {
+  return greedy_pass_impl(m, B, prompt, n_prompt, max_length, return_timestamps, check_every, tokens, stream, nullptr);
+}
+
+// decoder positions per captured graph / per interleave slot (KW_GRAPH_POS: A/B measurements)
+static const int GRAPH_POS = [] {
+  const char* e = getenv("KW_GRAPH_POS");
+  return e ? std::max(1, atoi(e)) : 8;
+}();
+
+static int greedy_pass_impl(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
+                            int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream,
+                            const std::function<int()>* between) {
   KW_TRY(bound_device_ok("kw_greedy_pass"));
   KW_REQUIRE(m && prompt && tokens, "kw_greedy_pass: null argument");
   KW_REQUIRE(n_prompt >= 1 && n_prompt <= 4, "kw_greedy_pass: prompt of %d tokens (1..4 supported)", n_prompt);
@@ -618,7 +635,6 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
   // stream — the caller's may be the legacy default stream, which cannot capture) and re-launched on every later pass
   // with the same shape; programmatic-launch edges are kept by the capture.  Not used while per-kernel profiling events
   // or the in-kernel timeline stamps are active (they would be baked into the graph).
-  constexpr int GRAPH_POS = 8;
   const unsigned per_kernel_prof = (1u << KW_PROF_DEC_GEMM) | (1u << KW_PROF_DEC_CROSS);
   if (g_decode_graph.load() && !(g_prof.mask & per_kernel_prof) && !getenv("KW_DECODE_SKIP")) {
     const int cfg_epoch = g_sample_fused.load() | (g_gemm_impl.load() << 1);
@@ -630,6 +646,7 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
     bool pre = false, stop = false;
     int pos = 0;
     while (pos + 1 < max_length && !stop) {
+      if (between) KW_TRY((*between)());
       const int end = std::min(pos + GRAPH_POS, max_length - 1);
       kw_model::PassGraph* pg = nullptr;
       for (auto& g : m->graphs)
@@ -705,6 +722,7 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
   }
   bool pre_embedded = false;
   for (int pos = 0; pos + 1 < max_length; ++pos) {
+    if (between && pos % GRAPH_POS == 0) KW_TRY((*between)());
     const int sample = pos >= n_prompt - 1;
     bool did_next = false;
     KW_TRY(decode_step(m, tokens, max_length, B, pos, n_prompt, sample, return_timestamps, m->finished, nullptr, st,
@@ -728,6 +746,48 @@ int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prom
   }
   if (pending_since >= 0) KW_CUDA_OK(cudaEventSynchronize(m->finished_copied));  // finished_host is reused by the next pass
   if (g_prof.mask & (1u << KW_PROF_DEC_PASS)) g_prof.work[KW_PROF_DEC_PASS] += pass_bytes;
+  return steps;
+}
+
+// Two batches in flight on one stream: the encoder of batch i + 1 (model `enc`) in layer groups, with the decoder
+// positions of batch i (model `dec`, whose encoder output is already in place) slotted between the groups, GRAPH_POS
+// positions at a time.  Same kernels and the same results as kw_encode(enc) + kw_greedy_pass(dec); what changes is the
+// power profile the clock governor sees: a ~140 ms block of power-capped GEMMs followed by a ~45 ms block of latency-bound
+// decode kernels leaves the SM clock low for the whole decode block, alternating ~9 ms / ~3 ms slices does not
+// (tools/interleave_probe.py).  `enc` and `dec` are two kw_model handles created over the same weight table (two
+// workspaces); dec == NULL runs the encoder alone (first batch of a stream).
+int kw_encode_decode(kw_model* enc, const float* mel, int32_t B_enc, kw_model* dec, int32_t B_dec, const int32_t* prompt,
+                     int32_t n_prompt, int32_t max_length, int32_t return_timestamps, int32_t check_every,
+                     int32_t* tokens, kw_stream stream) {
+  KW_TRY(bound_device_ok("kw_encode_decode"));
+  KW_REQUIRE(enc && mel, "kw_encode_decode: null argument");
+  KW_REQUIRE(enc != dec, "kw_encode_decode: the two batches need two model handles (two workspaces)");
+  KW_REQUIRE(B_enc >= 1 && B_enc <= enc->cfg.max_batch, "kw_encode_decode: B_enc=%d outside [1, max_batch=%d]", B_enc,
+             enc->cfg.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!dec) return kw_encode(enc, mel, B_enc, nullptr, stream);
+  KW_REQUIRE(prompt && tokens, "kw_encode_decode: null argument");
+  const int L = enc->cfg.enc_layers;
+  const int slots = std::max(1, (max_length - 1 + GRAPH_POS - 1) / GRAPH_POS);
+  const int per_slot = (L + slots - 1) / slots;
+  int next_layer = 0;
+  bool stem_done = false;
+  const std::function<int()> between = [&]() -> int {
+    if (!stem_done) {
+      KW_TRY(encode_stem(enc, mel, B_enc, st));
+      stem_done = true;
+    }
+    const int l1 = std::min(L, next_layer + per_slot);
+    KW_TRY(encode_layers(enc, B_enc, next_layer, l1, st));
+    next_layer = l1;
+    return KW_OK;
+  };
+  const int steps = greedy_pass_impl(dec, B_dec, prompt, n_prompt, max_length, return_timestamps, check_every, tokens,
+                                     stream, &between);
+  if (steps < 0) return steps;
+  if (!stem_done) KW_TRY(encode_stem(enc, mel, B_enc, st));
+  KW_TRY(encode_layers(enc, B_enc, next_layer, L, st));  // the decoder stopped early (every row finished)
+  KW_TRY(encode_finish(enc, B_enc, nullptr, st));
   return steps;
 }
 

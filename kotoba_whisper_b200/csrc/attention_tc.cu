@@ -34,11 +34,7 @@ constexpr int ATT_SM_WARPS = 4;                    // softmax warps: one thread 
 constexpr int ATT_SM_THREADS = ATT_SM_WARPS * 32;
 constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 1);   // + one warp whose lane 0 issues both the TMA loads and the MMAs
 constexpr uint32_t IDESC_S = make_idesc(128, ABK, 0, 0);
-#ifndef KW_ATT_H2
-#define KW_ATT_H2 0  // 1: P = exp2 computed as packed half-precision pairs (one MUFU op per two keys), P handed to the MMA as f16
-#endif
-// B = V is MN-major (head dim contiguous); with KW_ATT_H2 the A operand (P, from TMEM) is f16 while V stays bf16
-constexpr uint32_t IDESC_PV = make_idesc(128, 64, 0, 1) & ~(KW_ATT_H2 ? (1u << 7) : 0u);
+constexpr uint32_t IDESC_PV = make_idesc(128, 64, 0, 1);  // B = V is MN-major (head dim contiguous)
 
 struct AttnParams {
   bf16* out;
@@ -85,25 +81,11 @@ __device__ __forceinline__ float ex2_poly(float x) {  // scalar form: every cons
   return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
 }
 __device__ __forceinline__ float2 ex2_poly2(float2 x) { return make_float2(ex2_poly(x.x), ex2_poly(x.y)); }
-// two exponentials per MUFU instruction: the pair of fp32 exponents is rounded to f16x2 (|x| < 16 for every key that
-// matters: absolute error <= 2^-8 in the exponent, i.e. <= 0.27 % in p, the size of the bf16 rounding P used to get; f16 P
-// itself carries 11 significant bits against bf16's 8), exp2 on the packed pair, result is the packed P the MMA reads.
-__device__ __forceinline__ uint32_t ex2_h2(float lo, float hi) {
-  uint32_t h, y;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
-  return y;
-}
-__device__ __forceinline__ uint32_t hadd2_u(uint32_t a, uint32_t b) {
-  uint32_t y;
-  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b));
-  return y;
-}
-__device__ __forceinline__ float hsum2_u(uint32_t a) {
-  const __half2 h = *reinterpret_cast<const __half2*>(&a);
-  const float2 f = __half22float2(h);
-  return f.x + f.y;
-}
+// Measured and dropped in round 2: skipping the exp2 work of query rows past Tq (a warp of the last 128-row tile) and of
+// the key groups past Tk in the last key tile (4.4 % of the MUFU work in total): 760 / 666 TFLOP/s against 767 — the
+// extra control flow costs registers (109 / 128 against 106) and scheduling freedom in the loop that matters.
+// (Packed half-precision exponentials — ex2.approx.f16x2 / ex2.approx.ftz.bf16x2 — were checked as a way to halve the
+// MUFU work: ptxas lowers both to TWO scalar MUFU.EX2.F16 / .BF16 operations on sm_100a, so there is nothing to gain.)
 
 #ifndef KW_ATT3_KVS
 #define KW_ATT3_KVS 3
@@ -267,21 +249,6 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float alpha = moved ? ex2(mb_run - mb) : 1.0f;  // 0 on the first tile
       const float2 nmb = make_float2(-mb, -mb);
       ATT_T(2);
-#if KW_ATT_H2
-      uint32_t pk[ABK / 2];
-      uint32_t hs[4] = {0u, 0u, 0u, 0u};  // four f16x2 partial row sums of 8 pairs each (<= 8 * 2^8: exact range, 11-bit adds)
-#pragma unroll
-      for (int i = 0; i < ABK; i += 8) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(v[i + 2 * q]), __uint_as_float(v[i + 2 * q + 1])), L2, nmb);
-          const uint32_t pq = ex2_h2(x.x, x.y);  // exp2(-inf) = 0: masked keys
-          pk[(i >> 1) + q] = pq;
-          hs[q] = hadd2_u(hs[q], pq);
-        }
-      }
-      l_run = l_run * alpha + ((hsum2_u(hs[0]) + hsum2_u(hs[1])) + (hsum2_u(hs[2]) + hsum2_u(hs[3])));
-#else
       float2 rs0 = make_float2(0.0f, 0.0f), rs1 = make_float2(0.0f, 0.0f);
       uint32_t pk[ABK / 2];
 #pragma unroll
@@ -297,7 +264,6 @@ attn_tc3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         rs1 = __fadd2_rn(rs1, __fadd2_rn(e[1], e[3]));
       }
       l_run = l_run * alpha + ((rs0.x + rs0.y) + (rs1.x + rs1.y));
-#endif
       mb_run = mb;
       ATT_T(3);
       if (j > 0) {  // P(j-1) V(j-1) complete: the P columns are free again and O is stable

@@ -110,7 +110,7 @@ static inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 gr
   cfg.numAttrs = enabled ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
-// L2 eviction-priority policies for per-load cache hints and the bulk L2 prefetch
+// L2 eviction-priority policies for per-load cache hints
 __device__ __forceinline__ uint64_t l2_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
@@ -120,21 +120,6 @@ __device__ __forceinline__ uint64_t l2_evict_last() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
-}
-__device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {  // bytes % 16 == 0, ptr 16 B aligned
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-}
-// Spreads a strided set of regions over the CTAs of a launch: CTA `cta` of `n_cta` requests its share in <= 32 KB pieces.
-__device__ __forceinline__ void l2_prefetch_regions(const void* base, long long stride, int len, int n, int cta, int n_cta) {
-  if (!base || len <= 0) return;
-  constexpr int PIECE = 32768;
-  const int per_region = (len + PIECE - 1) / PIECE;
-  const int total = per_region * n;
-  for (int i = cta; i < total; i += n_cta) {
-    const int r = i / per_region, o = (i % per_region) * PIECE;
-    const int bytes = len - o < PIECE ? len - o : PIECE;
-    l2_prefetch_bulk(static_cast<const char*>(base) + (size_t)r * stride + o, (uint32_t)bytes & ~15u);
-  }
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -189,13 +174,7 @@ struct GemmArgs {
   int epi;
   kw_dtype a_type, w_type, out_type;
   const SampleFuse* sample;  // EPI_ARGMAX only
-  // decode-time (skinny) launches only.  l2pf_*: rows [0, l2pf_len bytes) of each of l2pf_n regions spaced l2pf_stride
-  // bytes apart are pulled into L2 by CTAs of this launch (cross-attention K/V of the NEXT cross-attention kernel: its
-  // HBM time moves under this latency-bound kernel).  w_hint: L2 eviction priority of the weight loads (0 normal,
-  // 1 evict_last, 2 evict_first).
-  const void* l2pf_base;
-  long long l2pf_stride;
-  int l2pf_len, l2pf_n, w_hint;
+  int w_hint;  // decode-time (skinny) launches: L2 eviction priority of the weight loads (0 normal, 1 evict_last, 2 evict_first)
 };
 
 int gemm_simt(const GemmArgs& g, cudaStream_t st);

@@ -41,9 +41,7 @@ struct Params {
   const float* pos;
   int M, N, K, ldo, pos_period, epi, out_bf16;
   SampleFuse sf;  // EPI_ARGMAX (decode-time vocabulary projection)
-  const void* l2pf_base;  // skinny kernel: L2 prefetch regions (GemmArgs) and weight-load eviction priority
-  long long l2pf_stride;
-  int l2pf_len, l2pf_n, w_hint;
+  int w_hint;  // skinny kernel: L2 eviction priority of the weight loads (GemmArgs::w_hint)
 };
 
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
@@ -636,8 +634,6 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         if (it % GROUP == 0) mbar_expect_tx(full_bar(g), group_bytes(it));
         load_w(base + it * STAGE_BYTES, full_bar(g), kcoord(it), tile_of(it) * BM);
       }
-      // this CTA's share of the L2 prefetch (behind its own first ring of weights in the request queue)
-      l2_prefetch_regions(p.l2pf_base, p.l2pf_stride, p.l2pf_len, p.l2pf_n, (int)blockIdx.x, (int)gridDim.x);
       stamp(1);
       asm volatile("griddepcontrol.wait;" ::: "memory");
       stamp(2);
@@ -886,7 +882,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.M = g.M; p.N = g.N; p.K = g.K; p.ldo = g.ldo; p.pos_period = g.pos_period > 0 ? g.pos_period : 1;
   p.epi = g.epi; p.out_bf16 = g.out_type == KW_BF16;
   memset(&p.sf, 0, sizeof(p.sf));
-  p.l2pf_base = g.l2pf_base; p.l2pf_stride = g.l2pf_stride; p.l2pf_len = g.l2pf_len; p.l2pf_n = g.l2pf_n; p.w_hint = g.w_hint;
+  p.w_hint = g.w_hint;
   if (g.epi == EPI_ARGMAX) {
     if (!g.sample || !(g.M <= sk::BN) || g.N <= 8192) return KW_ERR_UNSUPPORTED;  // R = 128 decode-time kernel only
     if (g.sample->tail0 % 32 != 0 || g.sample->n_part != 2 * ceil_div(g.sample->tail0, 128) || g.sample->tail0 > g.N ||

@@ -143,6 +143,7 @@ class WhisperB200ForConditionalGeneration:
         self._lib = _lib.load()
         self._keep: List[torch.Tensor] = []
         self._handle = C.c_void_p()
+        self._extra_handles: List[C.c_void_p] = []
         self._build(state_dict)
 
     # ---- construction ----------------------------------------------------------------------------------------------
@@ -242,12 +243,27 @@ class WhisperB200ForConditionalGeneration:
         rules = _lib.kw_token_rules(g.eos_token_id, g.pad_token_id, g.no_timestamps_token_id,
                                     -1 if g.max_initial_timestamp_index is None else g.max_initial_timestamp_index,
                                     sup_a, len(sup), bsup_a, len(bsup))
+        self._create_args = (cfg, w, rules, sup_a, bsup_a)
         with torch.cuda.device(dev):
             _lib.check(self._lib.kw_model_create(C.byref(cfg), C.byref(w), C.byref(rules), C.byref(self._handle)),
                        "kw_model_create")
 
+    def _new_handle(self) -> C.c_void_p:
+        """A second kw_model over the SAME weight tensors: its own workspace / KV pools, no second copy of the weights
+        (GenerateStream keeps two batches in flight)."""
+        cfg, w, rules, _, _ = self._create_args
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.kw_model_create(C.byref(cfg), C.byref(w), C.byref(rules), C.byref(h)), "kw_model_create")
+        self._extra_handles.append(h)
+        return h
+
     def __del__(self):
         try:
+            for h in getattr(self, "_extra_handles", []):
+                if h.value:
+                    self._lib.kw_model_destroy(h)
+            self._extra_handles = []
             if getattr(self, "_handle", None) and self._handle.value:
                 self._lib.kw_model_destroy(self._handle)
                 self._handle = C.c_void_p()
@@ -273,7 +289,7 @@ class WhisperB200ForConditionalGeneration:
         if input_features.dim() != 3 or input_features.shape[1] != c.num_mel_bins:
             raise ValueError(f"input_features must be [batch, {c.num_mel_bins}, frames], got {tuple(input_features.shape)}")
 
-    def encode(self, input_features: torch.Tensor, return_hidden: bool = True) -> Optional[torch.Tensor]:
+    def encode(self, input_features: torch.Tensor, return_hidden: bool = True, handle=None) -> Optional[torch.Tensor]:
         """[B, n_mels, 3000] -> fp32 [B, 1500, d] (WhisperEncoder.forward, modeling_whisper.py:593-647)."""
         c = self.config
         self._check_features(input_features)
@@ -291,19 +307,19 @@ class WhisperB200ForConditionalGeneration:
         out = torch.empty((B, c.max_source_positions, c.d_model), dtype=torch.float32, device=self.device) \
             if return_hidden else None
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.kw_encode(self._handle, mel.data_ptr(), B, out.data_ptr() if return_hidden else None,
-                                           self._stream()), "kw_encode")
+            _lib.check(self._lib.kw_encode(handle or self._handle, mel.data_ptr(), B,
+                                           out.data_ptr() if return_hidden else None, self._stream()), "kw_encode")
         self._last_mel = mel  # keep alive until the stream has consumed it
         return out
 
     def encode_output(self, input_features, **kwargs) -> EncoderOutput:
         return EncoderOutput(self.encode(input_features))
 
-    def _greedy_pass(self, B: int, prompt: List[int], max_length: int, return_timestamps: bool) -> np.ndarray:
+    def _greedy_pass(self, B: int, prompt: List[int], max_length: int, return_timestamps: bool, handle=None) -> np.ndarray:
         tokens = torch.empty((B, max_length), dtype=torch.int32, device=self.device)
         pr = (C.c_int32 * len(prompt))(*prompt)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.kw_greedy_pass(self._handle, B, pr, len(prompt), max_length, int(return_timestamps), 16,
+            _lib.check(self._lib.kw_greedy_pass(handle or self._handle, B, pr, len(prompt), max_length, int(return_timestamps), 16,
                                                 tokens.data_ptr(), self._stream()), "kw_greedy_pass")
         return tokens.cpu().numpy()
 
@@ -403,6 +419,10 @@ class WhisperB200ForConditionalGeneration:
                     raise ValueError(f"per-call generation_config.{k} differs from the list baked into the device "
                                      "token rules; build the model with that generation_config instead")
         c = self.config
+        # private (GenerateStream): plan only / first pass already done on another workspace handle
+        plan_only = kwargs.pop("_plan_only", False)
+        first_tokens = kwargs.pop("_first_pass_tokens", None)
+        handle = kwargs.pop("_handle", None) or self._handle
         encoder_outputs = kwargs.pop("encoder_outputs", None)
         max_length = kwargs.pop("max_length", None)
         max_new_tokens = kwargs.pop("max_new_tokens", None)
@@ -442,6 +462,8 @@ class WhisperB200ForConditionalGeneration:
         max_length = min(int(max_length), c.max_target_positions)
         if max_length <= len(prompt):
             raise ValueError(f"max_length={max_length} leaves no room after the {len(prompt)}-token prompt")
+        if plan_only:
+            return prompt, max_length, return_timestamps
 
         if not is_shortform and B > 1:
             if attention_mask is None:
@@ -458,10 +480,12 @@ class WhisperB200ForConditionalGeneration:
             nf = {b: min(max_frames[b] - seek[b], seg_frames) for b in rows}
             for c0 in range(0, len(rows), self.max_batch):
                 chunk = rows[c0:c0 + self.max_batch]
-                if encoder_outputs is not None:
+                if first_tokens is not None and n_pass == 0:
+                    pass  # GenerateStream: this chunk's encoder and first greedy pass already ran on `handle`
+                elif encoder_outputs is not None:
                     e = enc[chunk].to(device=self.device, dtype=torch.float32).contiguous()
                     with torch.cuda.device(self.device):
-                        _lib.check(self._lib.kw_set_encoder_output(self._handle, e.data_ptr(), len(chunk),
+                        _lib.check(self._lib.kw_set_encoder_output(handle, e.data_ptr(), len(chunk),
                                                                    self._stream()), "kw_set_encoder_output")
                     self._last_mel = e
                 else:
@@ -471,8 +495,9 @@ class WhisperB200ForConditionalGeneration:
                         seg = torch.zeros((len(chunk), c.num_mel_bins, seg_frames), dtype=feats.dtype, device=self.device)
                         for i, b in enumerate(chunk):
                             seg[i, :, : nf[b]] = feats[b, :, seek[b]: seek[b] + nf[b]]
-                    self.encode(seg, return_hidden=False)
-                toks = self._greedy_pass(len(chunk), prompt, max_length, return_timestamps)
+                    self.encode(seg, return_hidden=False, handle=handle)
+                toks = first_tokens if (first_tokens is not None and n_pass == 0) else \
+                    self._greedy_pass(len(chunk), prompt, max_length, return_timestamps, handle)
                 n_pass += 1
                 for i, b in enumerate(chunk):
                     seq = toks[i, len(prompt):].tolist()
@@ -504,6 +529,12 @@ class WhisperB200ForConditionalGeneration:
         if return_segments:
             return {"sequences": res, "segments": out}
         return res
+
+    def generate_stream(self, **generate_kwargs) -> "GenerateStream":
+        """Throughput mode of the labelling loop (`for batch in loader: ids = model.generate(batch, **kw)`,
+        run_pseudo_labelling.py:333-341): `stream.submit(batch)` returns the ids of the PREVIOUS batch, `stream.flush()`
+        the last ones.  Same arguments and results as `generate`; see GenerateStream."""
+        return GenerateStream(self, **generate_kwargs)
 
     # ---- teacher-forcing forward (distillation's frozen teacher) -----------------------------------------------------
     @torch.no_grad()
@@ -574,3 +605,85 @@ class WhisperB200ForConditionalGeneration:
     def cross_kv(self, B: int):
         with torch.cuda.device(self.device):
             _lib.check(self._lib.kw_cross_kv(self._handle, B, self._stream()), "kw_cross_kv")
+
+
+class GenerateStream:
+    """Two batches in flight on one GPU: while batch i is decoded, the encoder of batch i + 1 runs in layer groups between
+    its decoder positions (kw_encode_decode).  Results are identical to calling `model.generate(batch, **kwargs)` batch by
+    batch (same kernels on the same data; only their order on the stream changes); each batch's ids come back one call
+    later.  Why it is faster: after a ~140 ms block of power-capped encoder GEMMs the clock governor keeps the SM clock
+    low through the whole latency-bound decode block that follows; alternating short slices of both avoids that.
+
+        stream = model.generate_stream(language="ja", task="transcribe", return_timestamps=False, max_length=128)
+        for batch in loader:
+            ids = stream.submit(batch["input_features"])      # ids of the previous batch (None on the first call)
+            ...
+        ids = stream.flush()
+
+    Batches must be short-form ([B <= max_batch, n_mels, 3000]); with return_timestamps=True the first greedy pass of a
+    batch is pipelined and any further seek passes run when its result is collected."""
+
+    def __init__(self, model: WhisperB200ForConditionalGeneration, **generate_kwargs):
+        for k in ("encoder_outputs", "attention_mask", "input_features"):
+            if generate_kwargs.get(k) is not None:
+                raise ValueError(f"GenerateStream takes `{k}` per submit() / not at all")
+        self.model = model
+        self.kwargs = dict(generate_kwargs)
+        self.stats = self.kwargs.pop("stats", None)
+        self._handles = [model._handle, model._new_handle()]
+        self._slot = 0
+        self._pending = None  # (slot, features, tokens buffer or None)
+        self._plan = None
+
+    def _collect(self, pending, tokens: Optional[torch.Tensor]):
+        slot, feats, _ = pending
+        m, (prompt, max_length, ts) = self.model, self._plan
+        first = tokens.cpu().numpy()
+        st = {} if self.stats is not None else None
+        ids = m.generate(feats, _first_pass_tokens=first, _handle=self._handles[slot], stats=st, **self.kwargs)
+        if st is not None:
+            self.stats["passes"] = st.get("passes", 0)
+        return ids
+
+    def submit(self, input_features: torch.Tensor):
+        m, c = self.model, self.model.config
+        m._check_features(input_features)
+        B = input_features.shape[0]
+        if input_features.shape[-1] != 2 * c.max_source_positions or B > m.max_batch:
+            raise ValueError(f"GenerateStream batches must be [B <= {m.max_batch}, {c.num_mel_bins}, "
+                             f"{2 * c.max_source_positions}] short-form features, got {tuple(input_features.shape)}")
+        if self._plan is None:
+            self._plan = m.generate(input_features, _plan_only=True, **self.kwargs)
+        prompt, max_length, ts = self._plan
+        mel = input_features.to(device=m.device, dtype=torch.float32).contiguous()
+        prev = self._pending
+        pr = (C.c_int32 * len(prompt))(*prompt)
+        tokens = None
+        with torch.cuda.device(m.device):
+            if prev is None:
+                _lib.check(m._lib.kw_encode_decode(self._handles[self._slot], mel.data_ptr(), B, None, 0, pr, len(prompt),
+                                                   max_length, int(ts), 16, None, m._stream()), "kw_encode_decode")
+            else:
+                Bp = prev[1].shape[0]
+                tokens = torch.empty((Bp, max_length), dtype=torch.int32, device=m.device)
+                _lib.check(m._lib.kw_encode_decode(self._handles[self._slot], mel.data_ptr(), B, self._handles[prev[0]], Bp,
+                                                   pr, len(prompt), max_length, int(ts), 16, tokens.data_ptr(),
+                                                   m._stream()), "kw_encode_decode")
+        out = self._collect(prev, tokens) if prev is not None else None
+        self._pending = (self._slot, mel, None)
+        self._slot ^= 1
+        return out
+
+    def flush(self):
+        """Decodes the batch still in flight (plain greedy pass) and returns its ids; None when nothing is pending."""
+        prev, self._pending = self._pending, None
+        if prev is None:
+            return None
+        m = self.model
+        prompt, max_length, ts = self._plan
+        toks = m._greedy_pass(prev[1].shape[0], prompt, max_length, ts, self._handles[prev[0]])
+        st = {} if self.stats is not None else None
+        ids = m.generate(prev[1], _first_pass_tokens=toks, _handle=self._handles[prev[0]], stats=st, **self.kwargs)
+        if st is not None:
+            self.stats["passes"] = st.get("passes", 0)
+        return ids

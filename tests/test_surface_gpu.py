@@ -236,3 +236,36 @@ def test_logmel_producer_streams_slabs_in_order():
         seen += len(feats)
     assert seen == len(all_clips)
     assert prod.h2d_bytes == len(all_clips) * 480000 * 4 and prod.d2h_bytes == len(all_clips) * 80 * 3000 * 4
+
+
+# ---- two batches in flight: GenerateStream == generate, batch by batch -------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ts", [False, True])
+def test_generate_stream_equals_generate_batch_by_batch(dtype, ts):
+    from kotoba_whisper_b200 import WhisperFeatureExtractorB200
+    model, _ = build_pair(TINY, dtype, max_batch=4)
+    fe = WhisperFeatureExtractorB200(feature_size=128, device="cuda:0")
+    batches = [fe(clips(fam, seed), sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"]
+               for fam, seed in (("UGS", 11), ("GG", 12), ("SUGS", 13), ("U", 14))]   # ragged batch sizes 3, 2, 4, 1
+    kw = dict(language="ja", task="transcribe", return_timestamps=ts, max_length=40)
+    want = [model.generate(b, **kw).cpu() for b in batches]
+    stats = {}
+    stream = model.generate_stream(stats=stats, **kw)
+    got = []
+    for b in batches:
+        r = stream.submit(b)
+        if r is not None:
+            got.append(r.cpu())
+    got.append(stream.flush().cpu())
+    assert stream.flush() is None
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and torch.equal(g, w)
+    # a second run through the same stream object (handles and captured graphs reused)
+    assert stream.submit(batches[0]) is None
+    assert torch.equal(stream.submit(batches[1]).cpu(), want[0])
+    assert torch.equal(stream.flush().cpu(), want[1])
+    with pytest.raises(ValueError):
+        stream.submit(torch.zeros((5, 128, 3000), device="cuda:0"))   # > max_batch
+    with pytest.raises(ValueError):
+        stream.submit(torch.zeros((1, 128, 6000), device="cuda:0"))   # long-form
