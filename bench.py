@@ -204,12 +204,29 @@ def ours(args, rank: int, world: int, local_rank: int):
     gather = TokenGather(BATCH, MAX_LENGTH - 4, pad)
     inflight = {"h": None}
 
-    def step_resident():
+    gen_kw = dict(language="ja", task="transcribe", return_timestamps=False, max_length=MAX_LENGTH)
+
+    def step_plain():
         feats = fe.logmel_device(audio_dev)
-        ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=MAX_LENGTH,
-                             stats=stats)
+        ids = model.generate(feats, stats=stats, **gen_kw)
         prev, inflight["h"] = inflight["h"], gather.submit(ids)
         return (prev or inflight["h"]).result()
+
+    # Two batches in flight (GenerateStream): a step featurises batch i, runs its encoder with the decoder positions of
+    # batch i - 1 slotted between the layer groups, strips / gathers batch i - 1's ids.  Every step still does one
+    # log-mel, one encoder, one greedy pass and one gather; warm-up primes the stream, the batch left in flight after
+    # the timed steps is flushed outside (its decode replaces the one the first timed step did for the last warm-up batch).
+    stream = model.generate_stream(stats=stats, **gen_kw)
+
+    def step_stream():
+        feats = fe.logmel_device(audio_dev)
+        ids = stream.submit(feats)
+        if ids is None:
+            return None
+        prev, inflight["h"] = inflight["h"], gather.submit(ids)
+        return (prev or inflight["h"]).result()
+
+    step_resident = step_plain if args.no_stream else step_stream
 
     def step_e2e():
         feats = fe(clips_host, sampling_rate=SR, return_tensors="pt", keep_on_device=True)["input_features"]
@@ -258,12 +275,24 @@ def ours(args, rank: int, world: int, local_rank: int):
     ms_extra, _ = timed(step_resident, extra_steps)
     for c in (_lib.PROF_ENC_ATTN, _lib.PROF_DEC_CROSS, _lib.PROF_LOGMEL):
         prof[c] = _lib.profile_read(c, reset=True)
-    # whole decode pass (all kernels of all positions) under ONE event pair, so programmatic launch chains stay intact
+    last = stream.flush()
+    if last is not None:
+        gather.submit(last).result()
+    # whole decode pass (all kernels of all positions) under ONE event pair, so programmatic launch chains stay intact;
+    # measured batch by batch (plain generate): inside a stream step the pass is interleaved with the next encoder
+    step_plain()
     lib.kw_profile_enable(1 << _lib.PROF_DEC_PASS)
-    ms_pass_steps, _ = timed(step_resident, extra_steps)
+    ms_pass_steps, _ = timed(step_plain, extra_steps)
     prof[_lib.PROF_DEC_PASS] = _lib.profile_read(_lib.PROF_DEC_PASS, reset=True)
     lib.kw_profile_enable(0)
     passes = stats.get("passes", 0)
+    ms_plain, _ = timed(step_plain, args.steps)   # same work batch by batch, for comparison with the stream
+
+    def step_encoder_only():  # log-mel + encoder of one batch, no decode: what a stream step spends outside the decoder
+        model.encode(fe.logmel_device(audio_dev), return_hidden=False)
+
+    step_encoder_only()
+    ms_enc_only, _ = timed(step_encoder_only, args.steps)
 
     step_e2e()
     ms_e2e_serial, ids_host = timed(step_e2e, args.steps)
@@ -274,12 +303,16 @@ def ours(args, rank: int, world: int, local_rank: int):
     def run_e2e_pipelined(steps):
         out, h = None, None
         pending = fe.prefetch(clips_host, sampling_rate=SR, return_tensors="pt")
-        for i in range(steps):
-            feats = pending.result()["input_features"]
-            if i + 1 < steps:
-                pending = fe.prefetch(clips_host, sampling_rate=SR, return_tensors="pt")
-            ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False,
-                                 max_length=MAX_LENGTH)
+        for i in range(steps + 1):
+            if i < steps:
+                feats = pending.result()["input_features"]
+                if i + 1 < steps:
+                    pending = fe.prefetch(clips_host, sampling_rate=SR, return_tensors="pt")
+                ids = model.generate(feats, **gen_kw) if args.no_stream else stream.submit(feats)
+            else:
+                ids = None if args.no_stream else stream.flush()  # the stream starts and ends empty inside the timed region
+            if ids is None:
+                continue
             prev, h = h, gather.submit(ids)
             if prev is not None:
                 out = prev.result().cpu()  # batch i-1's gathered ids -> host while batch i's gather is in flight
@@ -329,11 +362,19 @@ def ours(args, rank: int, world: int, local_rank: int):
          "frac_nominal": p_gb / NOMINAL_GBS, "passes": pass_n, "share_of_step": p_share,
          "ms_per_position": pass_t / positions if positions else None,
          "algorithmic_bytes_per_position": pass_work / positions if positions else None},
+        {"kernel": "decode step inside the stream schedule (DERIVED: timed stream step minus a timed log-mel + encoder-only "
+                   "step, divided by the positions of one pass; includes the host-side strip / gather of the step)",
+         "bound": "hbm", "unit": "GB/s", "peak": hbm,
+         "achieved": (pass_work / max(pass_n, 1)) / 1e9 / max((ms - ms_enc_only) / args.steps / 1e3, 1e-9),
+         "frac": (pass_work / max(pass_n, 1)) / 1e9 / max((ms - ms_enc_only) / args.steps / 1e3, 1e-9) / hbm,
+         "ms_per_position": (ms - ms_enc_only) / args.steps / (MAX_LENGTH - 1),
+         "ms_encoder_only_step": ms_enc_only / args.steps} if not args.no_stream else None,
         {"kernel": "decode-step cross-attention", "bound": "hbm", "achieved": x_gb, "peak": hbm, "unit": "GB/s",
          "frac": x_gb / hbm, "frac_nominal": x_gb / NOMINAL_GBS, "launches": x_n, "share_of_step": x_share},
         {"kernel": "log-mel (stft+mel+log, incl. fix-up pass)", "bound": "hbm", "achieved": m_gb, "peak": hbm,
          "unit": "GB/s", "frac": m_gb / hbm, "frac_nominal": m_gb / NOMINAL_GBS, "launches": m_n, "share_of_step": m_share},
     ]
+    extra = [e for e in extra if e is not None]
     parity = None
     if not args.no_parity:
         # the benched run parity-checked in place: the same 64 clips and the same weights through the exact-fp32 CUDA path
@@ -360,7 +401,12 @@ def ours(args, rank: int, world: int, local_rank: int):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                       "passes_per_step": passes, "l2": "inputs_larger_than_l2 (123 MB audio + 1.5 GB weights per step)",
+                       "passes_per_step": passes,
+                       "schedule": "batch by batch" if args.no_stream else
+                       "2 batches in flight (GenerateStream: encoder of batch i+1 slotted between the decoder "
+                       "positions of batch i on one stream); every timed step = 1 log-mel + 1 encoder + 1 greedy pass "
+                       "+ 1 token gather",
+                       "ms_per_step_batch_by_batch": ms_plain / args.steps, "l2": "inputs_larger_than_l2 (123 MB audio + 1.5 GB weights per step)",
                        "tokens_out_shape": list(ids.shape)},
             "roofline": roofline, "roofline_extra": extra, "roofline_extra_note": f"timed with CUDA events in {extra_steps} extra steps after the timed region", "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "audio_s/s", "ms_per_step": ms_e2e / args.steps,
@@ -381,6 +427,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=1, help="clips per step of the bounded CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream", action="store_true", help="model.generate batch by batch instead of GenerateStream")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-place bf16-vs-fp32 token parity check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

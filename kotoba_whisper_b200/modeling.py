@@ -630,7 +630,10 @@ class GenerateStream:
         self.model = model
         self.kwargs = dict(generate_kwargs)
         self.stats = self.kwargs.pop("stats", None)
-        self._handles = [model._handle, model._new_handle()]
+        # one extra workspace per model, shared by every stream made from it (use one stream at a time)
+        if not model._extra_handles:
+            model._new_handle()
+        self._handles = [model._handle, model._extra_handles[0]]
         self._slot = 0
         self._pending = None  # (slot, features, tokens buffer or None)
         self._plan = None
