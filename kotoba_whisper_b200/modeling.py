@@ -355,6 +355,16 @@ class WhisperB200ForConditionalGeneration:
             toks.append(g.no_timestamps_token_id)
         return toks
 
+    @staticmethod
+    def _stripped_lengths(arr: np.ndarray, pad_id: int, eos_id: int) -> np.ndarray:
+        """Per row of generated ids [n, T]: the length left after HF's pad / eos stripping (generation_whisper.py:1063-1086:
+        a row that ends in pad loses as many trailing ids as it holds pads — one fewer when pad == eos — and then a final
+        eos), for all rows at once."""
+        n_pad = (arr == pad_id).sum(1) - (1 if pad_id == eos_id else 0)
+        length = arr.shape[1] - np.where(arr[:, -1] == pad_id, np.maximum(n_pad, 0), 0)
+        last = arr[np.arange(arr.shape[0]), np.maximum(length - 1, 0)]
+        return length - ((length > 0) & (last == eos_id))
+
     def _split_segments(self, seq: List[int], seek_num_frames: int):
         """generation_whisper.py:1976-2073 -> (token lists of the completed segments, seek advance in mel frames)."""
         tb = self.generation_config.no_timestamps_token_id + 1
@@ -499,18 +509,20 @@ class WhisperB200ForConditionalGeneration:
                 toks = first_tokens if (first_tokens is not None and n_pass == 0) else \
                     self._greedy_pass(len(chunk), prompt, max_length, return_timestamps, handle)
                 n_pass += 1
+                # strip padding keeping one eos, then the eos itself (:1063-1086) — lengths for the whole chunk at once;
+                # rows without timestamp tokens are one segment that consumes the whole window (no per-row Python)
+                arr = np.asarray(toks)[:, len(prompt):]
+                length = self._stripped_lengths(arr, g.pad_token_id, g.eos_token_id)
+                has_ts = (arr >= g.no_timestamps_token_id + 1).any(1)
                 for i, b in enumerate(chunk):
-                    seq = toks[i, len(prompt):].tolist()
-                    if seq[-1] == g.pad_token_id:  # strip padding, keeping one eos (:1063-1076)
-                        n_pad = sum(1 for t in seq if t == g.pad_token_id)
-                        if g.pad_token_id == g.eos_token_id:
-                            n_pad -= 1
-                        if n_pad:
-                            seq = seq[:-n_pad]
-                    if seq[-1] == g.eos_token_id:
-                        seq = seq[:-1]
-                    if not seq:
+                    n = int(length[i])
+                    if n <= 0:
                         seek[b] += nf[b]
+                        continue
+                    seq = arr[i, :n].tolist()
+                    if not has_ts[i]:
+                        seek[b] += nf[b]
+                        out[b].extend(seq)
                         continue
                     segs, adv = self._split_segments(seq, nf[b])
                     seek[b] += adv
@@ -521,11 +533,11 @@ class WhisperB200ForConditionalGeneration:
         if stats is not None:
             stats["passes"] = n_pass
         L = max((len(o) for o in out), default=0)
-        res = torch.full((B, L), g.pad_token_id, dtype=torch.long)
+        res_np = np.full((B, L), g.pad_token_id, dtype=np.int64)
         for b, o in enumerate(out):
             if o:
-                res[b, : len(o)] = torch.tensor(o, dtype=torch.long)
-        res = res.to(in_device)
+                res_np[b, : len(o)] = o
+        res = torch.from_numpy(res_np).to(in_device)
         if return_segments:
             return {"sequences": res, "segments": out}
         return res

@@ -102,3 +102,32 @@ def test_shard_range_is_a_partition():
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_stripped_lengths_match_per_row_rule():
+    """Vectorised pad / eos stripping == the per-row rule of generation_whisper.py:1063-1086."""
+    from kotoba_whisper_b200.modeling import WhisperB200ForConditionalGeneration as M
+    rng = np.random.default_rng(5)
+    for pad, eos in ((50257, 50257), (50256, 50257)):
+        rows = []
+        for _ in range(400):
+            T = 12
+            n = int(rng.integers(0, T + 1))
+            seq = rng.integers(0, 300, size=T)
+            if rng.random() < 0.7 and n < T:
+                seq[n] = eos
+                seq[n + 1:] = pad
+            if rng.random() < 0.2:
+                seq[int(rng.integers(0, T))] = pad   # a stray pad id in the middle
+            rows.append(seq)
+        arr = np.stack(rows)
+        got = M._stripped_lengths(arr, pad, eos)
+        for r, g in zip(rows, got):
+            seq = r.tolist()
+            if seq[-1] == pad:
+                n_pad = sum(1 for t in seq if t == pad) - (1 if pad == eos else 0)
+                if n_pad > 0:
+                    seq = seq[:-n_pad]
+            if seq and seq[-1] == eos:
+                seq = seq[:-1]
+            assert len(seq) == int(g)
