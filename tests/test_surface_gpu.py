@@ -143,6 +143,15 @@ def test_from_hf_model_and_pad():
         want = hf.generate(mel, language="ja", task="transcribe", return_timestamps=True, max_length=40, num_beams=1)
     got = model.generate(mel.cuda(), language="ja", task="transcribe", return_timestamps=True, max_length=40)
     assert torch.equal(got.cpu(), want)
+    # from_pretrained with the reference's keywords (run_pseudo_labelling.py:224-232) on a locally saved checkpoint
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        hf.generation_config._from_model_config = False   # a real checkpoint ships its own generation_config.json
+        hf.save_pretrained(d)
+        m2 = WhisperB200ForConditionalGeneration.from_pretrained(d, torch_dtype=torch.float32,
+                                                                 attn_implementation="sdpa", max_batch=4, device="cuda:0")
+    got2 = m2.generate(mel.cuda(), language="ja", task="transcribe", return_timestamps=True, max_length=40)
+    assert torch.equal(got2.cpu(), want)
     # .pad(): the collator's call (run_pseudo_labelling.py:154-158) — list of per-example features -> one batch
     fe = WhisperFeatureExtractorB200(feature_size=128, device="cuda:0")
     feats = fe(clips("GS", 11), sampling_rate=16000)["input_features"]

@@ -45,6 +45,16 @@ if "cfg3" in what:
         return m.generate(x, language="ja", task="transcribe", return_timestamps=True, max_length=128, stats=st).cpu()
     t, ids = timed(f)
     out["cfg3_teacher_bf16_b32_ts"] = {"s_per_batch": t, "rtfx": 32 * 30 / t, "passes": st.get("passes"), "ids_shape": list(ids.shape)}
+    # the same labelling loop with two batches in flight (GenerateStream: first pass of batch i under the encoder of i+1)
+    stream = m.generate_stream(language="ja", task="transcribe", return_timestamps=True, max_length=128)
+    def g():
+        x = fe(a, sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"]
+        r = stream.submit(x)
+        return None if r is None else r.cpu()
+    g()
+    t, _ = timed(g)
+    stream.flush()
+    out["cfg3_teacher_bf16_b32_ts_stream"] = {"s_per_batch": t, "rtfx": 32 * 30 / t}
     if "tf" in what:
         x = fe(a, sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"]
         labels = torch.randint(0, 50257, (32, 128), device=dev)

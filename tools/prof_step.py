@@ -17,6 +17,7 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--max-length", type=int, default=128)
 ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--steps", type=int, default=1)
+ap.add_argument("--stream", action="store_true", help="GenerateStream: the profiled region is one steady-state stream step")
 ap.add_argument("--enc-layers", type=int, default=0, help="shrink the encoder (same kernel shapes) for --set full captures")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -26,11 +27,17 @@ model = WhisperB200ForConditionalGeneration.from_state_dict(
     max_batch=a.batch, device=dev)
 fe = WhisperFeatureExtractorB200(feature_size=128, device=dev)
 audio = torch.from_numpy(synth_audio(a.batch, 1000)).to(dev)
+kw = dict(language="ja", task="transcribe", return_timestamps=False, max_length=a.max_length)
+stream = model.generate_stream(**kw) if a.stream else None
+if stream:
+    stream.submit(fe.logmel_device(audio))   # primes the stream: the profiled step has a decode to interleave
 torch.cuda.synchronize()
 torch.cuda.profiler.start()   # ncu --profile-from-start off: skip the random-init kernels
 for _ in range(a.steps):
     feats = fe.logmel_device(audio)
-    ids = model.generate(feats, language="ja", task="transcribe", return_timestamps=False, max_length=a.max_length)
+    ids = stream.submit(feats) if stream else model.generate(feats, **kw)
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
+if stream:
+    stream.flush()
 print("ok", tuple(ids.shape))
