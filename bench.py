@@ -191,7 +191,8 @@ def ours(args, rank: int, world: int, local_rank: int):
     # ONE state_dict for both arms: HF's own CPU initialisation under torch.manual_seed(0), shipped to
     # the GPU — the reference arm builds the identical model (reference_arm -> build_hf(KOTOBA, seed=0)).
     sd = {k: v.detach() for k, v in build_hf(KOTOBA, seed=0).state_dict().items()}
-    model = WhisperB200ForConditionalGeneration.from_state_dict(sd, cfg, dtype=torch.bfloat16, max_batch=BATCH, device=dev)
+    co = 1 if args.no_stream else max(1, args.coalesce)   # submitted 64-clip batches per device batch (GenerateStream)
+    model = WhisperB200ForConditionalGeneration.from_state_dict(sd, cfg, dtype=torch.bfloat16, max_batch=BATCH * co, device=dev)
     torch.cuda.empty_cache()
     fe = WhisperFeatureExtractorB200(feature_size=128, device=dev)
     audio_host = synth_audio(BATCH, seed=1000 * 1 + rank)       # seed = 1000*config + rank
@@ -212,11 +213,13 @@ def ours(args, rank: int, world: int, local_rank: int):
         prev, inflight["h"] = inflight["h"], gather.submit(ids)
         return (prev or inflight["h"]).result()
 
-    # Two batches in flight (GenerateStream): a step featurises batch i, runs its encoder with the decoder positions of
-    # batch i - 1 slotted between the layer groups, strips / gathers batch i - 1's ids.  Every step still does one
-    # log-mel, one encoder, one greedy pass and one gather; warm-up primes the stream, the batch left in flight after
-    # the timed steps is flushed outside (its decode replaces the one the first timed step did for the last warm-up batch).
-    stream = model.generate_stream(stats=stats, **gen_kw)
+    # Two device batches in flight (GenerateStream): a step featurises one 64-clip batch and submits it; every `co`-th
+    # submit launches the encoder of the `co` buffered batches as ONE device batch, with the decoder positions of the
+    # previous device batch slotted between the layer groups, and strips / gathers finished ids one 64-clip batch per
+    # step.  Over any `co` consecutive steps the GPU does `co` log-mels, encoder work for `co` x 64 clips, one greedy
+    # pass over `co` x 64 rows and `co` gathers; warm-up primes the stream, what is left in flight after the timed
+    # steps is flushed outside (its decode replaces the one the first timed launch did for the last warm-up batches).
+    stream = model.generate_stream(coalesce=co, stats=stats, **gen_kw)
 
     def step_stream():
         feats = fe.logmel_device(audio_dev)
@@ -258,6 +261,12 @@ def ours(args, rank: int, world: int, local_rank: int):
         sampler.start()
     for _ in range(args.warmup):
         step_resident()
+    if not args.no_stream:
+        # steady state before the timed region: a device batch in flight (so the first timed launch has a pass to
+        # interleave) and a buffer fill such that the K timed steps launch ceil(K / co) device batches — never fewer
+        # encoder / decoder rows than K x 64 (an odd K at co = 2 does the work of K + 1 batches: counted against us)
+        while stream.device_batches < 2 or (stream.buffered + args.steps) % co != 0:
+            step_resident()
     # Timed region: only the dominant kernel category (encoder GEMMs) carries CUDA-event pairs; the other categories
     # are timed the same way in two extra, untimed steps right after (event pairs between the decode kernels would
     # break the programmatic-dependent-launch overlap the timed region is supposed to measure).
@@ -275,8 +284,7 @@ def ours(args, rank: int, world: int, local_rank: int):
     ms_extra, _ = timed(step_resident, extra_steps)
     for c in (_lib.PROF_ENC_ATTN, _lib.PROF_DEC_CROSS, _lib.PROF_LOGMEL):
         prof[c] = _lib.profile_read(c, reset=True)
-    last = stream.flush()
-    if last is not None:
+    while (last := stream.flush()) is not None:
         gather.submit(last).result()
     # whole decode pass (all kernels of all positions) under ONE event pair, so programmatic launch chains stay intact;
     # measured batch by batch (plain generate): inside a stream step the pass is interleaved with the next encoder
@@ -284,6 +292,14 @@ def ours(args, rank: int, world: int, local_rank: int):
     lib.kw_profile_enable(1 << _lib.PROF_DEC_PASS)
     ms_pass_steps, _ = timed(step_plain, extra_steps)
     prof[_lib.PROF_DEC_PASS] = _lib.profile_read(_lib.PROF_DEC_PASS, reset=True)
+    prof_co = None
+    if co > 1:  # the coalesced pass alone: co x 64 rows through plain generate (same kernels the stream launches)
+        feats_co = torch.cat([fe.logmel_device(audio_dev) for _ in range(co)])
+        model.generate(feats_co, **gen_kw)
+        _lib.profile_read(_lib.PROF_DEC_PASS, reset=True)
+        timed(lambda: model.generate(feats_co, **gen_kw), extra_steps)
+        prof_co = _lib.profile_read(_lib.PROF_DEC_PASS, reset=True)
+        del feats_co
     lib.kw_profile_enable(0)
     passes = stats.get("passes", 0)
     ms_plain, _ = timed(step_plain, args.steps)   # same work batch by batch, for comparison with the stream
@@ -309,13 +325,15 @@ def ours(args, rank: int, world: int, local_rank: int):
                 if i + 1 < steps:
                     pending = fe.prefetch(clips_host, sampling_rate=SR, return_tensors="pt")
                 ids = model.generate(feats, **gen_kw) if args.no_stream else stream.submit(feats)
-            else:
-                ids = None if args.no_stream else stream.flush()  # the stream starts and ends empty inside the timed region
-            if ids is None:
-                continue
-            prev, h = h, gather.submit(ids)
-            if prev is not None:
-                out = prev.result().cpu()  # batch i-1's gathered ids -> host while batch i's gather is in flight
+                tail = [ids] if ids is not None else []
+            else:  # the stream starts and ends empty inside the timed region
+                tail = []
+                while not args.no_stream and (ids := stream.flush()) is not None:
+                    tail.append(ids)
+            for ids in tail:
+                prev, h = h, gather.submit(ids)
+                if prev is not None:
+                    out = prev.result().cpu()  # batch i-1's gathered ids -> host while batch i's gather is in flight
         return h.result().cpu()
 
     run_e2e_pipelined(2)
@@ -354,20 +372,37 @@ def ours(args, rank: int, world: int, local_rank: int):
                 "peak": tf_sus, "unit": "TFLOP/s", "frac": g_tf / tf_sus, "frac_burst": g_tf / tf_burst,
                 "frac_nominal": g_tf / NOMINAL_TF, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peak_src, "launches": g_n, "share_of_step": g_share}
+    # the coalesced pass (co x 64 rows per decoder position): weights and the vocabulary matrix are streamed once for all
+    # rows, so its algorithmic bytes per position are NOT co x the 64-row figure (kw_greedy_pass counts them per pass)
+    co_t, co_n, co_work = prof_co if prof_co else (pass_t, pass_n, pass_work)
+    co_positions = (MAX_LENGTH - 1) * max(co_n, 1)
+    co_gb = (co_work / 1e9) / (co_t / 1e3) if co_t > 0 else 0.0
+    dec_ms_per_step = max((ms - ms_enc_only) / args.steps, 1e-6)      # decode share of one 64-clip stream step
+    dec_work_per_step = co_work / max(co_n, 1) / co                    # algorithmic bytes of that share
     extra = [
         {"kernel": "encoder self-attention", "bound": "tensor", "achieved": a_tf, "peak": tf_sus, "unit": "TFLOP/s",
          "frac": a_tf / tf_sus, "frac_nominal": a_tf / NOMINAL_TF, "launches": a_n, "share_of_step": a_share},
-        {"kernel": "decode step (all kernels of a decoder position, whole greedy pass under one event pair)",
+        {"kernel": "decode step, 64 rows (all kernels of a decoder position, whole greedy pass under one event pair, "
+                   "batch by batch)",
          "bound": "hbm", "achieved": p_gb, "peak": hbm, "unit": "GB/s", "frac": p_gb / hbm,
          "frac_nominal": p_gb / NOMINAL_GBS, "passes": pass_n, "share_of_step": p_share,
          "ms_per_position": pass_t / positions if positions else None,
          "algorithmic_bytes_per_position": pass_work / positions if positions else None},
+        {"kernel": f"decode step, {co * BATCH} rows (the coalesced pass the stream schedule runs: {co} submitted batches "
+                   "per device batch; whole greedy pass alone under one event pair)",
+         "bound": "hbm", "achieved": co_gb, "peak": hbm, "unit": "GB/s", "frac": co_gb / hbm,
+         "frac_nominal": co_gb / NOMINAL_GBS, "passes": co_n,
+         "ms_per_position": co_t / co_positions if co_positions else None,
+         "ms_per_pass_per_64_clips": co_t / max(co_n, 1) / co,
+         "algorithmic_bytes_per_position": co_work / co_positions if co_positions else None} if prof_co else None,
         {"kernel": "decode step inside the stream schedule (DERIVED: timed stream step minus a timed log-mel + encoder-only "
-                   "step, divided by the positions of one pass; includes the host-side strip / gather of the step)",
+                   "step = the decode share of one 64-clip step, against the algorithmic bytes of the coalesced pass "
+                   "divided by the batches it covers; includes the host-side strip / gather of the step)",
          "bound": "hbm", "unit": "GB/s", "peak": hbm,
-         "achieved": (pass_work / max(pass_n, 1)) / 1e9 / max((ms - ms_enc_only) / args.steps / 1e3, 1e-9),
-         "frac": (pass_work / max(pass_n, 1)) / 1e9 / max((ms - ms_enc_only) / args.steps / 1e3, 1e-9) / hbm,
-         "ms_per_position": (ms - ms_enc_only) / args.steps / (MAX_LENGTH - 1),
+         "achieved": dec_work_per_step / 1e9 / (dec_ms_per_step / 1e3),
+         "frac": dec_work_per_step / 1e9 / (dec_ms_per_step / 1e3) / hbm,
+         "ms_decode_share_per_step": dec_ms_per_step,
+         "ms_per_position": dec_ms_per_step * co / (MAX_LENGTH - 1),
          "ms_encoder_only_step": ms_enc_only / args.steps} if not args.no_stream else None,
         {"kernel": "decode-step cross-attention", "bound": "hbm", "achieved": x_gb, "peak": hbm, "unit": "GB/s",
          "frac": x_gb / hbm, "frac_nominal": x_gb / NOMINAL_GBS, "launches": x_n, "share_of_step": x_share},
@@ -403,9 +438,11 @@ def ours(args, rank: int, world: int, local_rank: int):
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": f"dp{world}",
                        "passes_per_step": passes,
                        "schedule": "batch by batch" if args.no_stream else
-                       "2 batches in flight (GenerateStream: encoder of batch i+1 slotted between the decoder "
-                       "positions of batch i on one stream); every timed step = 1 log-mel + 1 encoder + 1 greedy pass "
-                       "+ 1 token gather",
+                       f"GenerateStream(coalesce={co}): every step submits one 64-clip batch; {co} submitted batches run as "
+                       f"one {co * BATCH}-row device batch, 2 device batches in flight (encoder of device batch i+1 "
+                       "slotted between the decoder positions of device batch i on one stream); per 64-clip step: 1 "
+                       f"log-mel + encoder work for 64 clips + 1/{co} of a {co * BATCH}-row greedy pass + 1 token gather",
+                       "coalesce": co, "device_batch": co * BATCH,
                        "ms_per_step_batch_by_batch": ms_plain / args.steps, "l2": "inputs_larger_than_l2 (123 MB audio + 1.5 GB weights per step)",
                        "tokens_out_shape": list(ids.shape)},
             "roofline": roofline, "roofline_extra": extra, "roofline_extra_note": f"timed with CUDA events in {extra_steps} extra steps after the timed region", "cpu_baseline": cpu,
@@ -422,12 +459,14 @@ def ours(args, rank: int, world: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-batch", type=int, default=1, help="clips per step of the bounded CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream", action="store_true", help="model.generate batch by batch instead of GenerateStream")
+    ap.add_argument("--coalesce", type=int, default=2,
+                    help="submitted 64-clip batches run as one device batch by GenerateStream (1 = the round-2 schedule)")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-place bf16-vs-fp32 token parity check")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -440,7 +440,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Decode-time ("skinny") variant: M = batch <= 64 rows of activations against a weight matrix that is read exactly once.
+// Decode-time ("skinny") variant: M = batch <= 64 (or <= 128) rows of activations against a weight matrix that is read exactly once.
 // The product is computed transposed, out^T[N, M] = W[N,K] . A[M,K]^T, so the 128-row MMA dimension streams weight
 // rows and the batch is the N = 64 dimension: R x 64 x K tiles, a deep TMA ring (this kernel is bound by how fast one SM
 // can pull bytes, ~50 GB/s per CTA measured), two 64-column TMEM accumulators.
@@ -455,27 +455,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // that all four epilogue warps write whole 16-byte groups of one batch row; bias / residual values are requested in that
 // same layout before the accumulator wait.
 namespace sk {
-constexpr int BM = 128, BN = 64;  // MMA shape: 128 weight rows x 64 batch columns
+constexpr int BM = 128;       // MMA M: weight rows
+constexpr int MAX_BN = 128;   // MMA N: batch rows, 64 or 128 (template parameter BN of the kernel)
 constexpr int MAX_SPLIT = 4;
 // R = weight rows actually loaded (and produced) per tile.  R = 32 quarters the bytes per stage, so small-N projections
 // spread over 4x more CTAs; the MMA still runs at M = 128 and simply reads stale shared memory for rows R..127, whose
 // accumulator rows are never read back.
-template <int R> struct Cfg {
+// BN = 128 (batches of 65..128 rows: two coalesced 64-utterance batches decode as one, the per-position latency chain
+// is paid once for both): activation tiles double, so the rings are shallower; everything else is the same kernel.
+template <int R, int BN> struct Cfg {
   static constexpr int A_BYTES = R * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = R == 32 ? 12 : R == 40 ? 10 : 8;
+  static constexpr int STAGES = BN == 64 ? (R == 32 ? 12 : R == 40 ? 10 : 8) : (R == 128 ? 4 : 8);
   // k-block slots that share one full / empty mbarrier pair (one wait + fence per group on the MMA-issuing thread)
   static constexpr int GROUP = R == 32 ? 4 : 2;  // (STAGES is a multiple of GROUP)
   static constexpr int RING = STAGES * STAGE_BYTES + (BM - R) * BK * 2;  // + tail the M = 128 read of the last stage may touch
-  static constexpr int SLOTS = R == 32 ? MAX_SPLIT : 1;                  // split-K partial slots (R = 32 only)
-  // [slot][batch row][feature] fp32; R = 128 (vocabulary): + one float of pitch per row and 768 B of rule tables for the
-  // fused arg-max epilogue (EPI_ARGMAX)
-  static constexpr int OUT_STAGE = SLOTS * BN * R * 4 + (R == 128 ? BN * 4 + 768 : 0);
+  static constexpr int SLOTS = R == 32 ? (BN == 64 ? MAX_SPLIT : 3) : 1;  // split-K partial slots (R = 32 only)
+  // [slot][batch row][feature] fp32; R = 128 (vocabulary): + one float of pitch per row, the per-row column masks and
+  // 512 B of lane bits for the fused arg-max epilogue (EPI_ARGMAX)
+  static constexpr int OUT_STAGE = SLOTS * BN * R * 4 + (R == 128 ? 2 * BN * 4 + 512 : 0);
   static constexpr size_t SMEM_BYTES = 1024 + (size_t)RING + 512 + OUT_STAGE;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulators
+  static constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
+  static_assert(STAGES % GROUP == 0 && STAGE_BYTES % 1024 == 0 && A_BYTES % 1024 == 0, "ring layout");
+  static_assert(SMEM_BYTES <= 232448, "skinny GEMM smem budget");
 };
-static_assert(Cfg<32>::SMEM_BYTES <= 232448 && Cfg<40>::SMEM_BYTES <= 232448 && Cfg<128>::SMEM_BYTES <= 232448,
-              "skinny GEMM smem budget");
-constexpr int TMEM_COLS = 128;
-constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
+template struct Cfg<32, 64>; template struct Cfg<40, 64>; template struct Cfg<128, 64>;
+template struct Cfg<32, 128>; template struct Cfg<40, 128>; template struct Cfg<128, 128>;
 }  // namespace sk
 
 __device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
@@ -490,11 +495,12 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
 // Coalesced half of the skinny epilogue for one tile: V consecutive features of one batch row per item, items spread
 // over the 128 epilogue threads.  `stage` = [n_slots][64][R] fp32 partial sums, `res` = residual values preloaded in the
 // same item order (EPI_RESID, V = 4 only).
-template <int R, int V, int EPI, bool OUT_BF16>
+template <int R, int BN, int V, int EPI, bool OUT_BF16>
 __device__ __forceinline__ void skinny_store(const Params& p, const float* stage, int n_slots, int n0, int tid,
                                              const float4* res, const float4& bias4) {
-  constexpr int GROUPS = R / V, ITEMS = sk::BN * GROUPS, PER = ITEMS / (SK_EPI_WARPS * 32);
-  constexpr int UNROLL = PER <= 4 ? PER : 4;  // res[i] (PER = 4) needs the full unroll; longer loops keep registers down
+  constexpr int GROUPS = R / V, ITEMS = BN * GROUPS, PER = ITEMS / (SK_EPI_WARPS * 32);
+  // res[i] (R = 32, V = 4: PER = BN / 16) needs the full unroll; longer loops keep registers down
+  constexpr int UNROLL = (R == 32 && V == 4) ? PER : PER <= 4 ? PER : 4;
 #pragma unroll UNROLL
   for (int i = 0; i < PER; ++i) {
     const int idx = tid + i * SK_EPI_WARPS * 32, row = idx / GROUPS, f = (idx % GROUPS) * V, n = n0 + f;
@@ -504,7 +510,7 @@ __device__ __forceinline__ void skinny_store(const Params& p, const float* stage
     for (int e = 0; e < V; ++e) v[e] = stage[row * R + f + e];
     for (int sl = 1; sl < n_slots; ++sl) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) v[e] += stage[(sl * sk::BN + row) * R + f + e];
+      for (int e = 0; e < V; ++e) v[e] += stage[(sl * BN + row) * R + f + e];
     }
     if (V == 4 && R == 32) {  // every item of a thread covers the same 4 features: one bias group, requested up front
       v[0] += bias4.x; v[1] += bias4.y; v[V - 2] += bias4.z; v[V - 1] += bias4.w;
@@ -537,28 +543,28 @@ __device__ __forceinline__ void skinny_store(const Params& p, const float* stage
   }
 }
 
-template <int R, int V>
+template <int R, int BN, int V>
 __device__ __forceinline__ void skinny_store_dispatch(const Params& p, const float* stage, int n_slots, int n0, int tid,
                                                       const float4* res, const float4& bias4) {
   if (p.out_bf16) {
-    if (p.epi == EPI_GELU) skinny_store<R, V, EPI_GELU, true>(p, stage, n_slots, n0, tid, res, bias4);
-    else skinny_store<R, V, EPI_STORE, true>(p, stage, n_slots, n0, tid, res, bias4);
+    if (p.epi == EPI_GELU) skinny_store<R, BN, V, EPI_GELU, true>(p, stage, n_slots, n0, tid, res, bias4);
+    else skinny_store<R, BN, V, EPI_STORE, true>(p, stage, n_slots, n0, tid, res, bias4);
   } else {
-    if (p.epi == EPI_GELU) skinny_store<R, V, EPI_GELU, false>(p, stage, n_slots, n0, tid, res, bias4);
-    else if (p.epi == EPI_RESID) skinny_store<R, V, EPI_RESID, false>(p, stage, n_slots, n0, tid, res, bias4);
-    else skinny_store<R, V, EPI_STORE, false>(p, stage, n_slots, n0, tid, res, bias4);
+    if (p.epi == EPI_GELU) skinny_store<R, BN, V, EPI_GELU, false>(p, stage, n_slots, n0, tid, res, bias4);
+    else if (p.epi == EPI_RESID) skinny_store<R, BN, V, EPI_RESID, false>(p, stage, n_slots, n0, tid, res, bias4);
+    else skinny_store<R, BN, V, EPI_STORE, false>(p, stage, n_slots, n0, tid, res, bias4);
   }
 }
 
-template <int R>
+template <int R, int BN>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const Params p,
                       const int vec) {
-  using C = sk::Cfg<R>;
-  constexpr int BM = R, BN = sk::BN, STAGES = C::STAGES, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES;
+  using C = sk::Cfg<R, BN>;
+  constexpr int BM = R, STAGES = C::STAGES, A_BYTES = C::A_BYTES, STAGE_BYTES = C::STAGE_BYTES;
   constexpr int GROUP = C::GROUP;  // barrier g serves slots [g*GROUP, (g+1)*GROUP)
-  constexpr int TMEM_COLS = sk::TMEM_COLS;
-  constexpr uint32_t IDESC = sk::IDESC;
+  constexpr int TMEM_COLS = C::TMEM_COLS;
+  constexpr uint32_t IDESC = C::IDESC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -569,7 +575,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gen_base + C::RING + 8 * (2 * STAGES + 4));
-  float* out_stage = reinterpret_cast<float*>(gen_base + C::RING + 512);  // [slot][64][R]
+  float* out_stage = reinterpret_cast<float*>(gen_base + C::RING + 512);  // [slot][BN][R]
   const uint32_t out_stage_u32 = base + C::RING + 512;
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -743,31 +749,35 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         mbar_arrive(tempty_bar(as));
         asm volatile("bar.sync 1, 128;" ::: "memory");  // tile + lane bits staged
         if (t * BM < p.sf.tail0) {                      // tiles that hold text ids emit partials
-          const int b = tid & (BN - 1), half = tid >> 6, cm = s_cm[b];
-          const float* row = s_tile + b * TP + half * 64;
-          const int* lbs = s_lb + half * 64;
-          float best = -INFINITY;
-          int bi = -1;
+          // BN = 64: thread = (batch row, half tile); BN = 128: thread = batch row, both halves in turn
+#pragma unroll
+          for (int hh = 0; hh < BN / 64; ++hh) {
+            const int b = BN == 64 ? (tid & 63) : tid, half = BN == 64 ? (tid >> 6) : hh, cm = s_cm[b];
+            const float* row = s_tile + b * TP + half * 64;
+            const int* lbs = s_lb + half * 64;
+            float best = -INFINITY;
+            int bi = -1;
 #pragma unroll 16
-          for (int k = 0; k < 64; ++k) {
-            const float x = row[k];
-            const bool take = !(lbs[k] & cm) && x > best;  // strict: the first (smallest) id wins a tie
-            best = take ? x : best;
-            bi = take ? k : bi;
+            for (int k = 0; k < 64; ++k) {
+              const float x = row[k];
+              const bool take = !(lbs[k] & cm) && x > best;  // strict: the first (smallest) id wins a tie
+              best = take ? x : best;
+              bi = take ? k : bi;
+            }
+            if (b < p.M)
+              p.sf.vpart[(size_t)b * p.sf.n_part + t * 2 + half] =
+                  make_float2(best, __int_as_float(bi >= 0 ? t * BM + half * 64 + bi : p.N));
           }
-          if (b < p.M)
-            p.sf.vpart[(size_t)b * p.sf.n_part + t * 2 + half] =
-                make_float2(best, __int_as_float(bi >= 0 ? t * BM + half * 64 + bi : p.N));
         }
         if (tcount + 1 < my_tiles) asm volatile("bar.sync 1, 128;" ::: "memory");  // staging free for the next tile
         if (threadIdx.x == 0) stamp(tcount == 0 ? 9 : (tcount + 1 < my_tiles ? 5 : 6));
         continue;
       }
-      // EPI_RESID: this thread's residual groups are requested before the accumulator wait (R = 32: 4 x 16 bytes)
-      float4 res[R == 32 ? 4 : 1];
+      // EPI_RESID: this thread's residual groups are requested before the accumulator wait (R = 32: BN / 16 x 16 bytes)
+      float4 res[R == 32 ? BN / 16 : 1];
       if (R == 32 && p.epi == EPI_RESID && vec == 4 && rank == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < BN / 16; ++i) {
           const int idx = tid + i * 128, row = idx / 8, n = t * BM + (idx % 8) * 4;
           res[i] = (row < p.M && n < p.N)
                        ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo + n)
@@ -805,9 +815,9 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
       mbar_arrive(tempty_bar(as));
       if (S == 1) {
         asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffer complete
-        if (vec == 4) skinny_store_dispatch<R, 4>(p, out_stage, 1, t * BM, tid, res, bias4);
-        else if (vec == 2) skinny_store_dispatch<R, 2>(p, out_stage, 1, t * BM, tid, res, bias4);
-        else skinny_store_dispatch<R, 1>(p, out_stage, 1, t * BM, tid, res, bias4);
+        if (vec == 4) skinny_store_dispatch<R, BN, 4>(p, out_stage, 1, t * BM, tid, res, bias4);
+        else if (vec == 2) skinny_store_dispatch<R, BN, 2>(p, out_stage, 1, t * BM, tid, res, bias4);
+        else skinny_store_dispatch<R, BN, 1>(p, out_stage, 1, t * BM, tid, res, bias4);
         if (tcount + 1 < my_tiles) asm volatile("bar.sync 1, 128;" ::: "memory");  // buffer free for the next tile
         if (threadIdx.x == 0) stamp(5 + (tcount == 0 ? 0 : 1));
       } else {
@@ -816,9 +826,9 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         if (rank == 0) {
           asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
           if (threadIdx.x == 0) stamp(10);
-          if (vec == 4) skinny_store_dispatch<R, 4>(p, out_stage, S, t * BM, tid, res, bias4);
-          else if (vec == 2) skinny_store_dispatch<R, 2>(p, out_stage, S, t * BM, tid, res, bias4);
-          else skinny_store_dispatch<R, 1>(p, out_stage, S, t * BM, tid, res, bias4);
+          if (vec == 4) skinny_store_dispatch<R, BN, 4>(p, out_stage, S, t * BM, tid, res, bias4);
+          else if (vec == 2) skinny_store_dispatch<R, BN, 2>(p, out_stage, S, t * BM, tid, res, bias4);
+          else skinny_store_dispatch<R, BN, 1>(p, out_stage, S, t * BM, tid, res, bias4);
           if (threadIdx.x == 0) stamp(5);
         }
       }
@@ -856,7 +866,7 @@ void gemm_tc_set_2cta(int on) { tc::g_use_2cta = on; }
 int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   using namespace tc;
   if (g.a_type != KW_BF16 || g.w_type != KW_BF16) return KW_ERR_UNSUPPORTED;
-  const bool skinny = g.M <= sk::BN && g.epi != EPI_GELU_POS;
+  const bool skinny = g.M <= sk::MAX_BN && g.epi != EPI_GELU_POS;
   if (g.K % BK != 0 || g.lda % 8 != 0 || g.M < 1) return KW_ERR_UNSUPPORTED;
   if (!skinny && (g.N % 32 != 0 || g.ldo % 8 != 0 || ((uintptr_t)g.out & 15))) return KW_ERR_UNSUPPORTED;
   if (((uintptr_t)g.A & 15) || ((uintptr_t)g.W & 15)) return KW_ERR_UNSUPPORTED;
@@ -868,12 +878,12 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     KW_CUDA_OK(cudaGetDevice(&dev));
     KW_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sk::Cfg<32>::SMEM_BYTES));
-    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<40>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sk::Cfg<40>::SMEM_BYTES));
-    KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)sk::Cfg<128>::SMEM_BYTES));
+#define KW_SK_ATTR(R_, BN_)                                                                                    \
+  KW_CUDA_OK(cudaFuncSetAttribute(gemm_tc_skinny_kernel<R_, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)sk::Cfg<R_, BN_>::SMEM_BYTES))
+    KW_SK_ATTR(32, 64); KW_SK_ATTR(40, 64); KW_SK_ATTR(128, 64);
+    KW_SK_ATTR(32, 128); KW_SK_ATTR(40, 128); KW_SK_ATTR(128, 128);
+#undef KW_SK_ATTR
     attr = true;
   }
   Params p;
@@ -884,21 +894,22 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   memset(&p.sf, 0, sizeof(p.sf));
   p.w_hint = g.w_hint;
   if (g.epi == EPI_ARGMAX) {
-    if (!g.sample || !(g.M <= sk::BN) || g.N <= 8192) return KW_ERR_UNSUPPORTED;  // R = 128 decode-time kernel only
+    if (!g.sample || !(g.M <= sk::MAX_BN) || g.N <= 8192) return KW_ERR_UNSUPPORTED;  // R = 128 decode-time kernel only
     if (g.sample->tail0 % 32 != 0 || g.sample->n_part != 2 * ceil_div(g.sample->tail0, 128) || g.sample->tail0 > g.N ||
         g.sample->tail_ld < g.N - g.sample->tail0)
       return KW_ERR_ARG;
     p.sf = *g.sample;
   }
   CUtensorMap tmA, tmB;
-  if (g.M <= sk::BN && g.epi != EPI_GELU_POS) {  // decode-time shape: weights stream through the 128-row dimension
+  if (skinny) {  // decode-time shape: weights stream through the 128-row dimension, the batch is the MMA's N (64 or 128)
+    const int bn = g.M <= 64 ? 64 : 128;
     // small projections: 32 weight rows per CTA tile -> 4x the CTAs in flight; 40 rows when 32-row tiles would spill
     // into a second wave by a few tiles (fc1: N = 5120 -> 160 tiles on 148 SMs took 15.3 us, 128 tiles of 40 rows one wave)
     int R = g.N <= 8192 ? 32 : 128;
     if (R == 32 && ceil_div(g.N, 32) > n_sm && ceil_div(g.N, 40) <= n_sm) R = 40;
     int rc = make_map(&tmB, g.W, g.N, g.K, g.K, R);
     if (rc) return rc;
-    if ((rc = make_map(&tmA, g.A, g.M, g.K, g.lda, sk::BN))) return rc;
+    if ((rc = make_map(&tmA, g.A, g.M, g.K, g.lda, bn))) return rc;
     const int tiles = ceil_div(g.N, R);
     static const int pdl_gemm = [] {
       const char* e = getenv("KW_PDL_GEMM");
@@ -911,7 +922,7 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     // split-K over a cluster when the tiles alone leave most SMs idle (N = 1280 projections: 40 tiles -> 120 CTAs)
     int split = 1;
     if (R == 32)
-      for (int s2 = max_split; s2 > 1; --s2)
+      for (int s2 = std::min(max_split, bn == 64 ? sk::Cfg<32, 64>::SLOTS : sk::Cfg<32, 128>::SLOTS); s2 > 1; --s2)
         if (tiles * s2 <= n_sm && g.K / BK >= 4 * s2) { split = s2; break; }
     // widest store the output layout allows: V features of one batch row per 16 / 8 / 4-byte (fp32) store
     const int esz = g.out_type == KW_BF16 ? 2 : 4;
@@ -922,7 +933,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(split > 1 ? tiles * split : std::min(tiles, n_sm));
     cfg.blockDim = dim3(SK_THREADS);
-    cfg.dynamicSmemBytes = R == 32 ? sk::Cfg<32>::SMEM_BYTES : R == 40 ? sk::Cfg<40>::SMEM_BYTES : sk::Cfg<128>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = bn == 64 ? (R == 32 ? sk::Cfg<32, 64>::SMEM_BYTES : R == 40 ? sk::Cfg<40, 64>::SMEM_BYTES : sk::Cfg<128, 64>::SMEM_BYTES)
+                                    : (R == 32 ? sk::Cfg<32, 128>::SMEM_BYTES : R == 40 ? sk::Cfg<40, 128>::SMEM_BYTES : sk::Cfg<128, 128>::SMEM_BYTES);
     cfg.stream = st;
     cudaLaunchAttribute attrs[2];
     int na = 0;
@@ -940,9 +952,15 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     }
     cfg.attrs = attrs;
     cfg.numAttrs = na;
-    if (R == 32) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<32>, tmB, tmA, p, vec));
-    else if (R == 40) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<40>, tmB, tmA, p, vec));
-    else KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<128>, tmB, tmA, p, vec));
+    if (bn == 64) {
+      if (R == 32) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<32, 64>, tmB, tmA, p, vec));
+      else if (R == 40) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<40, 64>, tmB, tmA, p, vec));
+      else KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<128, 64>, tmB, tmA, p, vec));
+    } else {
+      if (R == 32) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<32, 128>, tmB, tmA, p, vec));
+      else if (R == 40) KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<40, 128>, tmB, tmA, p, vec));
+      else KW_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_skinny_kernel<128, 128>, tmB, tmA, p, vec));
+    }
     KW_LAUNCH_OK();
     ++g_launches;
     return KW_OK;

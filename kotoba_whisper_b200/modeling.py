@@ -620,57 +620,86 @@ class WhisperB200ForConditionalGeneration:
 
 
 class GenerateStream:
-    """Two batches in flight on one GPU: while batch i is decoded, the encoder of batch i + 1 runs in layer groups between
-    its decoder positions (kw_encode_decode).  Results are identical to calling `model.generate(batch, **kwargs)` batch by
-    batch (same kernels on the same data; only their order on the stream changes); each batch's ids come back one call
-    later.  Why it is faster: after a ~140 ms block of power-capped encoder GEMMs the clock governor keeps the SM clock
-    low through the whole latency-bound decode block that follows; alternating short slices of both avoids that.
+    """Two device batches in flight on one GPU: while batch i is decoded, the encoder of batch i + 1 runs in layer groups
+    between its decoder positions (kw_encode_decode).  Results are identical to calling `model.generate(batch, **kwargs)`
+    batch by batch (same kernels on the same data; only their order on the stream changes); each batch's ids come back a
+    few calls later.  Why it is faster: after a ~140 ms block of power-capped encoder GEMMs the clock governor keeps the
+    SM clock low through the whole latency-bound decode block that follows; alternating short slices of both avoids that.
+
+    `coalesce=k` (k * batch <= model.max_batch): k submitted batches are run as ONE device batch.  A decoder position
+    is a chain of ~25 dependent, latency-bound kernels whose cost hardly depends on the number of rows (the weights are
+    streamed once per position either way), so decoding 128 utterances at a time nearly halves the per-utterance cost
+    of everything but the cross-attention K/V stream.  Utterances are independent rows of every kernel: the ids of a
+    batch do not depend on what it was grouped with (tests/test_surface_gpu.py).
 
         stream = model.generate_stream(language="ja", task="transcribe", return_timestamps=False, max_length=128)
         for batch in loader:
-            ids = stream.submit(batch["input_features"])      # ids of the previous batch (None on the first call)
+            ids = stream.submit(batch["input_features"])      # ids of the oldest finished batch (None while priming)
             ...
-        ids = stream.flush()
+        while (ids := stream.flush()) is not None:             # one batch per call, in submission order
+            ...
 
     Batches must be short-form ([B <= max_batch, n_mels, 3000]); with return_timestamps=True the first greedy pass of a
     batch is pipelined and any further seek passes run when its result is collected."""
 
-    def __init__(self, model: WhisperB200ForConditionalGeneration, **generate_kwargs):
+    def __init__(self, model: WhisperB200ForConditionalGeneration, coalesce: int = 1, **generate_kwargs):
         for k in ("encoder_outputs", "attention_mask", "input_features"):
             if generate_kwargs.get(k) is not None:
                 raise ValueError(f"GenerateStream takes `{k}` per submit() / not at all")
+        if int(coalesce) < 1:
+            raise ValueError(f"coalesce={coalesce} must be >= 1")
         self.model = model
+        self.coalesce = int(coalesce)
         self.kwargs = dict(generate_kwargs)
         self.stats = self.kwargs.pop("stats", None)
+        self._want_segments = bool(self.kwargs.pop("return_segments", False))
         # one extra workspace per model, shared by every stream made from it (use one stream at a time)
         if not model._extra_handles:
             model._new_handle()
         self._handles = [model._handle, model._extra_handles[0]]
         self._slot = 0
-        self._pending = None  # (slot, features, tokens buffer or None)
+        self._pending = None  # (slot, features of the device batch, sizes of the submitted batches inside it)
         self._plan = None
+        self._buf: List[torch.Tensor] = []   # submitted batches waiting for their group to fill
+        self._ready: List = []               # finished per-batch results, oldest first
+        self.device_batches = 0              # device batches launched so far
 
-    def _collect(self, pending, tokens: Optional[torch.Tensor]):
-        slot, feats, _ = pending
-        m, (prompt, max_length, ts) = self.model, self._plan
-        first = tokens.cpu().numpy()
+    @property
+    def buffered(self) -> int:
+        """Submitted batches whose group (coalesce > 1) has not been launched yet."""
+        return len(self._buf)
+
+    def _finish(self, pending, first_tokens):
+        """Host side of a device batch whose first greedy pass is done: strip / segment (and seek passes with timestamps),
+        then one result per submitted batch, exactly as `generate` packs it."""
+        slot, feats, sizes = pending
+        m = self.model
         st = {} if self.stats is not None else None
-        ids = m.generate(feats, _first_pass_tokens=first, _handle=self._handles[slot], stats=st, **self.kwargs)
+        res = m.generate(feats, _first_pass_tokens=first_tokens, _handle=self._handles[slot], stats=st,
+                         return_segments=True, **self.kwargs)
         if st is not None:
             self.stats["passes"] = st.get("passes", 0)
-        return ids
+        pad, b0 = m.generation_config.pad_token_id, 0
+        for n in sizes:
+            rows = res["segments"][b0:b0 + n]
+            b0 += n
+            L = max((len(o) for o in rows), default=0)
+            arr = np.full((n, L), pad, dtype=np.int64)
+            for i, o in enumerate(rows):
+                if o:
+                    arr[i, : len(o)] = o
+            ids = torch.from_numpy(arr).to(feats.device)
+            self._ready.append({"sequences": ids, "segments": rows} if self._want_segments else ids)
 
-    def submit(self, input_features: torch.Tensor):
-        m, c = self.model, self.model.config
-        m._check_features(input_features)
-        B = input_features.shape[0]
-        if input_features.shape[-1] != 2 * c.max_source_positions or B > m.max_batch:
-            raise ValueError(f"GenerateStream batches must be [B <= {m.max_batch}, {c.num_mel_bins}, "
-                             f"{2 * c.max_source_positions}] short-form features, got {tuple(input_features.shape)}")
-        if self._plan is None:
-            self._plan = m.generate(input_features, _plan_only=True, **self.kwargs)
+    def _launch(self):
+        """Launches the buffered group as one device batch (its encoder, interleaved with the greedy pass of the device
+        batch in flight) and finishes the batch that was in flight."""
+        m = self.model
+        sizes = [int(t.shape[0]) for t in self._buf]
+        mel = self._buf[0] if len(self._buf) == 1 else torch.cat(self._buf, 0)
+        self._buf = []
+        B = mel.shape[0]
         prompt, max_length, ts = self._plan
-        mel = input_features.to(device=m.device, dtype=torch.float32).contiguous()
         prev = self._pending
         pr = (C.c_int32 * len(prompt))(*prompt)
         tokens = None
@@ -684,21 +713,36 @@ class GenerateStream:
                 _lib.check(m._lib.kw_encode_decode(self._handles[self._slot], mel.data_ptr(), B, self._handles[prev[0]], Bp,
                                                    pr, len(prompt), max_length, int(ts), 16, tokens.data_ptr(),
                                                    m._stream()), "kw_encode_decode")
-        out = self._collect(prev, tokens) if prev is not None else None
-        self._pending = (self._slot, mel, None)
+        self.device_batches += 1
+        self._pending = (self._slot, mel, sizes)
         self._slot ^= 1
-        return out
+        if prev is not None:
+            self._finish(prev, tokens.cpu().numpy())
+
+    def submit(self, input_features: torch.Tensor):
+        m, c = self.model, self.model.config
+        m._check_features(input_features)
+        B = input_features.shape[0]
+        held = sum(int(t.shape[0]) for t in self._buf)
+        if input_features.shape[-1] != 2 * c.max_source_positions or held + B > m.max_batch:
+            raise ValueError(f"GenerateStream batches must be [B, {c.num_mel_bins}, {2 * c.max_source_positions}] "
+                             f"short-form features with coalesce x B <= max_batch = {m.max_batch}, got "
+                             f"{tuple(input_features.shape)} (coalesce={self.coalesce}, {held} rows already buffered)")
+        if self._plan is None:
+            self._plan = m.generate(input_features, _plan_only=True, **self.kwargs)
+        self._buf.append(input_features.to(device=m.device, dtype=torch.float32).contiguous())
+        if len(self._buf) >= self.coalesce:
+            self._launch()
+        return self._ready.pop(0) if self._ready else None
 
     def flush(self):
-        """Decodes the batch still in flight (plain greedy pass) and returns its ids; None when nothing is pending."""
-        prev, self._pending = self._pending, None
-        if prev is None:
-            return None
-        m = self.model
-        prompt, max_length, ts = self._plan
-        toks = m._greedy_pass(prev[1].shape[0], prompt, max_length, ts, self._handles[prev[0]])
-        st = {} if self.stats is not None else None
-        ids = m.generate(prev[1], _first_pass_tokens=toks, _handle=self._handles[prev[0]], stats=st, **self.kwargs)
-        if st is not None:
-            self.stats["passes"] = st.get("passes", 0)
-        return ids
+        """Finishes what is still in flight and returns the ids of ONE batch per call, oldest first; None when the stream
+        is empty (`while (ids := stream.flush()) is not None`).  With coalesce = 1 a single call returns the last batch."""
+        if not self._ready and self._buf:
+            self._launch()       # a group that did not fill: its own (smaller) device batch
+        if not self._ready and self._pending is not None:
+            prev, self._pending = self._pending, None
+            prompt, max_length, ts = self._plan
+            toks = self.model._greedy_pass(prev[1].shape[0], prompt, max_length, ts, self._handles[prev[0]])
+            self._finish(prev, toks)
+        return self._ready.pop(0) if self._ready else None

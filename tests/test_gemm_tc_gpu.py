@@ -29,7 +29,11 @@ SHAPES = [(128, 256, 64), (256, 512, 128), (100, 128, 128), (1500, 1280, 1280), 
           # cluster split-K (N <= ~1500: tiles x split <= 148 CTAs): uneven k-ranges, 2- and 3-way, 8 / 4-byte store paths
           (64, 1280, 1280), (5, 1000, 832), (7, 1282, 512), (3, 333, 1280), (40, 1536, 1024),
           # 40-row tiles (32-row tiles would need a second wave on 148 SMs): exact and ragged last tile, 8 / 4-byte stores
-          (64, 5120, 1280), (7, 5040, 256), (5, 4762, 128)]
+          (64, 5120, 1280), (7, 5040, 256), (5, 4762, 128),
+          # 65..128 batch rows (coalesced decode batches): the same kernel with the batch as a 128-wide MMA N; every tile
+          # height (32 with 2- / 3-way split-K, 40, 128), ragged batch and feature tails
+          (128, 1280, 1280), (128, 3840, 1280), (128, 5120, 1280), (128, 1280, 5120), (128, 51866, 1280), (65, 1280, 1280),
+          (100, 1282, 512), (97, 5040, 256), (127, 333, 1280), (96, 51866, 1280)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
@@ -59,13 +63,29 @@ def test_gemm_tc_matches_torch(M, N, K):
 def test_skinny_split_k_is_deterministic():
     """The split-K partials are added in rank order by one CTA (no atomics): repeated launches give identical bits."""
     torch.manual_seed(5)
-    A = torch.randn(64, 5120, device="cuda").bfloat16()
-    W = (torch.randn(1280, 5120, device="cuda") * 0.05).bfloat16()
-    b = torch.randn(1280, device="cuda")
-    x0 = torch.randn(64, 1280, device="cuda")
-    first = _run(A, W, b, 2, F32, out=x0.clone())
-    for _ in range(5):
-        assert torch.equal(_run(A, W, b, 2, F32, out=x0.clone()), first)
+    for M in (64, 128):
+        A = torch.randn(M, 5120, device="cuda").bfloat16()
+        W = (torch.randn(1280, 5120, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(1280, device="cuda")
+        x0 = torch.randn(M, 1280, device="cuda")
+        first = _run(A, W, b, 2, F32, out=x0.clone())
+        for _ in range(5):
+            assert torch.equal(_run(A, W, b, 2, F32, out=x0.clone()), first)
+
+
+def test_skinny_rows_do_not_depend_on_batch_width():
+    """A batch row's result is the same bits whether it is computed in a 64-wide or a 128-wide launch (same k order, fp32
+    accumulation per output element): coalescing two decode batches into one cannot change a token."""
+    torch.manual_seed(11)
+    for N, K, epi, ot in ((1280, 1280, 2, F32), (3840, 1280, 0, F32), (5120, 1280, 1, BF16), (1280, 5120, 2, F32), (51866, 1280, 0, F32)):
+        A = torch.randn(128, K, device="cuda").bfloat16()
+        W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+        b = torch.randn(N, device="cuda")
+        x0 = torch.randn(128, N, device="cuda") if epi == 2 else None
+        wide = _run(A, W, b, epi, ot, out=x0.clone() if x0 is not None else None)
+        lo = _run(A[:64].contiguous(), W, b, epi, ot, out=x0[:64].clone() if x0 is not None else None)
+        hi = _run(A[64:].contiguous(), W, b, epi, ot, out=x0[64:].clone() if x0 is not None else None)
+        assert torch.equal(wide[:64], lo) and torch.equal(wide[64:], hi), (N, K, epi)
 
 
 def test_gemm_tc_full_batch_shape_linearity():

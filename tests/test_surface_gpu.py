@@ -278,3 +278,62 @@ def test_generate_stream_equals_generate_batch_by_batch(dtype, ts):
         stream.submit(torch.zeros((5, 128, 3000), device="cuda:0"))   # > max_batch
     with pytest.raises(ValueError):
         stream.submit(torch.zeros((1, 128, 6000), device="cuda:0"))   # long-form
+
+
+# ---- coalesced decode batches: k submitted batches run as one device batch, ids unchanged ----------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("ts", [False, True])
+def test_generate_stream_coalesce_equals_batch_by_batch(dtype, ts):
+    from kotoba_whisper_b200 import WhisperFeatureExtractorB200
+    model, _ = build_pair(TINY, dtype, max_batch=8)
+    fe = WhisperFeatureExtractorB200(feature_size=128, device="cuda:0")
+    batches = [fe(clips(fam, seed), sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"]
+               for fam, seed in (("UGS", 21), ("GG", 22), ("SUGS", 23), ("U", 24), ("GU", 25))]   # ragged sizes, odd count
+    kw = dict(language="ja", task="transcribe", return_timestamps=ts, max_length=40)
+    want = [model.generate(b, **kw).cpu() for b in batches]
+    stream = model.generate_stream(coalesce=2, **kw)
+    got = []
+    for b in batches:
+        r = stream.submit(b)
+        if r is not None:
+            got.append(r.cpu())
+    assert stream.device_batches == 2 and stream.buffered == 1
+    while (r := stream.flush()) is not None:
+        got.append(r.cpu())
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and torch.equal(g, w)
+    with pytest.raises(ValueError):
+        stream.submit(torch.zeros((9, 128, 3000), device="cuda:0"))   # > max_batch
+    with pytest.raises(ValueError):
+        model.generate_stream(coalesce=0, **kw)
+
+
+def test_kotoba_bf16_coalesced_128_row_decode_is_row_identical():
+    """The benchmarked schedule: two 64-utterance batches decoded as one 128-row device batch (decode-time GEMMs with the
+    batch as a 128-wide MMA N, fused vocabulary epilogue over 128 rows).  Every utterance's ids must be the bits a
+    64-row `generate` gives: rows are independent in every kernel and the k order of a row's dot products is the same."""
+    from kotoba_whisper_b200 import WhisperB200ForConditionalGeneration, WhisperFeatureExtractorB200
+    from _gpu_util import state_dict_for
+    from _synth import KOTOBA, clip
+    sd, cfg = state_dict_for(tuple(sorted(KOTOBA.items())))
+    model = WhisperB200ForConditionalGeneration.from_state_dict(sd, cfg, dtype=torch.bfloat16, max_batch=128, device="cuda:0")
+    fe = WhisperFeatureExtractorB200(feature_size=128, device="cuda:0")
+    audio = [clip("UGSG"[i % 4], 9000 + i) for i in range(128)]
+    halves = [fe(audio[i:i + 64], sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"]
+              for i in (0, 64)]
+    for ts in (False, True):
+        kw = dict(language="ja", task="transcribe", return_timestamps=ts, max_length=64)
+        want = [model.generate(h, **kw).cpu() for h in halves]
+        both = model.generate(torch.cat(halves), **kw).cpu()          # plain 128-row generate
+        pad = model.generation_config.pad_token_id
+        for i, w in enumerate(want):
+            g = both[64 * i: 64 * (i + 1)]
+            L = max(w.shape[1], 1)
+            assert torch.equal(g[:, :w.shape[1]], w) and bool((g[:, w.shape[1]:] == pad).all()), (ts, i, L)
+        stream = model.generate_stream(coalesce=2, **kw)
+        assert stream.submit(halves[0]) is None and stream.submit(halves[1]) is None
+        got = []
+        while (r := stream.flush()) is not None:
+            got.append(r.cpu())
+        assert len(got) == 2 and all(torch.equal(g, w) for g, w in zip(got, want)), ts
