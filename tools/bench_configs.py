@@ -55,6 +55,15 @@ if "cfg3" in what:
     t, _ = timed(g)
     stream.flush()
     out["cfg3_teacher_bf16_b32_ts_stream"] = {"s_per_batch": t, "rtfx": 32 * 30 / t}
+    # coalesced: 4 submitted 32-clip batches run as one 128-row device batch (both greedy passes at 128 rows)
+    del stream, m
+    torch.cuda.empty_cache()
+    m = build(dict(KOTOBA, decoder_layers=32), torch.bfloat16, 128)
+    stream = m.generate_stream(coalesce=4, language="ja", task="transcribe", return_timestamps=True, max_length=128)
+    for _ in range(8): g()
+    t, _ = timed(g, reps=8, warm=0)
+    while stream.flush() is not None: pass
+    out["cfg3_teacher_bf16_b32_ts_coalesce4"] = {"s_per_batch": t, "rtfx": 32 * 30 / t, "device_batch": 128}
     if "tf" in what:
         x = fe(a, sampling_rate=16000, return_tensors="pt", keep_on_device=True)["input_features"]
         labels = torch.randint(0, 50257, (32, 128), device=dev)
@@ -78,6 +87,17 @@ if "cfg4" in what or "lat" in what:
             out["cfg4_longform_1h_chunk15_b64_" + ("device_chunker" if mode else "host_chunker")] = {
                 "s_total": t, "rtfx": 60 * minutes / t, "merged_tokens": len(toks), "windows": st.get("windows"),
                 "h2d_bytes": st.get("h2d_bytes")}
+        # 128 windows per generate call: the decode-time kernels take up to 128 rows (the latency chain of a decoder
+        # position is paid once for twice the rows)
+        m128 = build(KOTOBA, torch.bfloat16, 128); st = {}
+        def f128():
+            return transcribe_longform(m128, fe, audio, chunk_length_s=15, batch_size=128, language="ja", task="transcribe",
+                                       max_new_tokens=124, device_chunker=True, stats=st)
+        t, toks128 = timed(f128, reps=1, warm=1)
+        out["cfg4_longform_1h_chunk15_b128_device_chunker"] = {
+            "s_total": t, "rtfx": 60 * minutes / t, "merged_tokens": len(toks128), "windows": st.get("windows"),
+            "same_tokens_as_b64": list(toks128) == list(toks)}
+        del m128
     if "lat" in what:
         # run_speed_eval.py: batch size 1, chunk_length_s=15, one synthetic clip (rand-0.5)*2*0.007 of `duration` s,
         # language/task in generate_kwargs, wall clock around the whole pipeline call, 1 warm-up + 10 trials
