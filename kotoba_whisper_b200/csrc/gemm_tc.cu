@@ -30,8 +30,12 @@ constexpr int N_EPI_WARPS = KW_EPI_WARPS, THREADS = 32 * (N_EPI_WARPS + 2);  // 
 constexpr int EPI_THREADS = N_EPI_WARPS * 32, EPI_COLS = BN / (N_EPI_WARPS / 4);  // 64 columns per epilogue warp
 constexpr int SK_EPI_WARPS = 4, SK_THREADS = 32 * (SK_EPI_WARPS + 2);  // skinny kernel
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_STAGE_LD = 20, EPI_STAGE_FLOATS = 32 * EPI_STAGE_LD;  // per-warp transpose buffer: 32 rows x 16 cols (+4 pad)
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + 2 * BN * 4 /*bias*/ +
+// per-warp staging block of the residual epilogue: 32 rows x 16 cols, either dense with the tensor map's 64 B swizzle
+// (TMA reduction: 2 KB, 512 B aligned) or padded to 20 floats per row (read-modify-write path)
+constexpr int EPI_STAGE_LD = 20, EPI_STAGE_FLOATS = 32 * EPI_STAGE_LD;
+constexpr int EPI_STAGE_OFF = 256 /*barriers*/ + 2 * BN * 4 /*bias*/ + 256 /*pad: staging blocks 512 B aligned*/;
+static_assert(EPI_STAGE_OFF % 512 == 0 && (EPI_STAGE_FLOATS * 4) % 512 == 0, "TMA reduce staging alignment");
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_STAGE_OFF +
                               KW_EPI_WARPS * EPI_STAGE_FLOATS * 4 /*residual epilogue staging*/;
 
 struct Params {
@@ -42,6 +46,7 @@ struct Params {
   int M, N, K, ldo, pos_period, epi, out_bf16;
   SampleFuse sf;  // EPI_ARGMAX (decode-time vocabulary projection)
   int w_hint;  // skinny kernel: L2 eviction priority of the weight loads (GemmArgs::w_hint)
+  int resid_tma;  // wide kernels, EPI_RESID: 1 = x += tile as a TMA reduction at the L2, 0 = read-modify-write by the epilogue warps
 };
 
 constexpr uint32_t IDESC = make_idesc(BM, BN, 0, 0);
@@ -93,9 +98,9 @@ __device__ __forceinline__ void umma(uint32_t d, uint64_t a, uint64_t b, uint32_
 // n0 + 64*cgrp .. +64, in chunks of 16 columns (tcgen05.ld x16) to keep the register footprint of 16 epilogue warps
 // under the 113-register budget of a 576-thread CTA.  Waits for the accumulator (tfull), then TMEM -> registers -> bias /
 // GELU / residual / position add -> 16-byte global stores.  Shared by the 1-CTA and 2-CTA kernels.
-__device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc, int m0, int n0, int quarter, int cgrp,
-                                              int lane, float* s_bias_stage, float* s_stage, uint32_t tfull_addr,
-                                              uint32_t tfull_parity) {
+__device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap* tmO, uint32_t tmem_acc, int m0, int n0,
+                                              int quarter, int cgrp, int lane, float* s_bias_stage, float* s_stage,
+                                              uint32_t tfull_addr, uint32_t tfull_parity) {
   const int row = m0 + quarter * 32 + lane;
   const bool row_ok = row < p.M;
   constexpr int NCH = EPI_COLS / 16;
@@ -120,7 +125,13 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
                     : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  if (p.epi == EPI_RESID) {
+  // EPI_RESID, default: the add is not done here at all.  Each 32 x 16 block of (accumulator + bias) is written to the
+  // warp's staging block and handed to the L2 as ONE fp32 TMA reduction (cp.reduce.async.bulk.tensor .add): no residual
+  // loads, no load latency to hide, half the SM <-> L2 bytes, the same single rounding fl(x + fl(acc + bias)) per
+  // element.  tools/micro/tma_reduce_bench.cu: bulk add.f32 over the 491 MB stream runs at the HBM roof (5.5 TB/s
+  // read + write), like a fully pipelined read-modify-write.
+  const bool resid_rmw = p.epi == EPI_RESID && !p.resid_tma;
+  if (resid_rmw) {
     if (row_ok) {
       // the chunks that are not register-prefetched are at least pulled into L2 while the MMAs of this tile still run
       const char* rp = reinterpret_cast<const char*>(reinterpret_cast<const float*>(p.out) + (size_t)row * p.ldo + n0 +
@@ -151,6 +162,26 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    if (p.epi == EPI_RESID && p.resid_tma) {
+      const float4* b4p = reinterpret_cast<const float4*>(s_bias_stage + c * 16);
+      // the TMA engine has read the previous block out of this warp's staging memory
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      const int sw = (lane >> 1) & 3;  // CU_TENSOR_MAP_SWIZZLE_64B: 16-byte chunk index ^= address bits [7:8] = (row >> 1) & 3
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 b4 = b4p[j];
+        *reinterpret_cast<float4*>(s_stage + lane * 16 + ((j ^ sw) << 2)) =
+            make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {  // rows >= M and columns >= N are clipped by the tensor map
+        tma_reduce_add_2d(tmO, smem_u32(s_stage), col0, m0 + quarter * 32);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      continue;
+    }
     if (p.epi == EPI_RESID) {
       const float4* b4p = reinterpret_cast<const float4*>(s_bias_stage + c * 16);
       __syncwarp();  // previous chunk's coalesced reads of the staging buffer are done
@@ -224,7 +255,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, uint32_t tmem_acc
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t bar0 = base + STAGES * STAGE_BYTES;
@@ -311,11 +343,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tcount) {
       const int m0 = (t / tiles_n) * BM, n0 = (t % tiles_n) * BN;
       const uint32_t as = tcount & 1;
-      epilogue_tile(p, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN,
-                    s_bias + 2 * BN + warp * EPI_STAGE_FLOATS, tfull_bar(as), (tcount >> 1) & 1);
+      epilogue_tile(p, &tmO, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN,
+                    s_bias + (EPI_STAGE_OFF - 256) / 4 + warp * EPI_STAGE_FLOATS, tfull_bar(as), (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tempty_bar(as));  // one arrival per epilogue thread hands the accumulator back to the MMA warp
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's TMA reductions have landed
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -335,12 +368,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 namespace c2 {
 constexpr int STAGES = 6;
 constexpr int A_BYTES = 128 * BK * 2, B_BYTES = 128 * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;  // per CTA: 32 KB
-constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + 256 + 2 * BN * 4 + KW_EPI_WARPS * EPI_STAGE_FLOATS * 4;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)STAGES * STAGE_BYTES + EPI_STAGE_OFF + KW_EPI_WARPS * EPI_STAGE_FLOATS * 4;
 constexpr uint32_t IDESC = make_idesc(256, BN, 0, 0);
 }  // namespace c2
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmO, const Params p) {
   constexpr int STAGES = c2::STAGES, A_BYTES = c2::A_BYTES, STAGE_BYTES = c2::STAGE_BYTES;
   constexpr uint32_t IDESC = c2::IDESC;
   extern __shared__ uint8_t smem_raw[];
@@ -427,11 +461,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int t = pair; t < n_tiles; t += n_pairs, ++tcount) {
       const int m0 = (t / tiles_n) * 256 + (int)rank * 128, n0 = (t % tiles_n) * BN;
       const uint32_t as = tcount & 1;
-      epilogue_tile(p, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN,
-                    s_bias + 2 * BN + warp * EPI_STAGE_FLOATS, tfull_bar(as), (tcount >> 1) & 1);
+      epilogue_tile(p, &tmO, tmem_base + as * BN, m0, n0, quarter, cgrp, lane, s_bias + as * BN,
+                    s_bias + (EPI_STAGE_OFF - 256) / 4 + warp * EPI_STAGE_FLOATS, tfull_bar(as), (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive_cluster(mapa_u32(tempty_bar(as), 0));  // both CTAs' epilogue threads hand the accumulator back
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's TMA reductions have landed
   }
 
   tc_fence_before();
@@ -893,6 +928,11 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   p.epi = g.epi; p.out_bf16 = g.out_type == KW_BF16;
   memset(&p.sf, 0, sizeof(p.sf));
   p.w_hint = g.w_hint;
+  static const int resid_tma = [] {  // KW_RESID_TMA=0: read-modify-write residual epilogue (A/B measurements)
+    const char* e = getenv("KW_RESID_TMA");
+    return e ? atoi(e) : 1;
+  }();
+  p.resid_tma = 0;
   if (g.epi == EPI_ARGMAX) {
     if (!g.sample || !(g.M <= sk::MAX_BN) || g.N <= 8192) return KW_ERR_UNSUPPORTED;  // R = 128 decode-time kernel only
     if (g.sample->tail0 % 32 != 0 || g.sample->n_part != 2 * ceil_div(g.sample->tail0, 128) || g.sample->tail0 > g.N ||
@@ -900,7 +940,16 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
       return KW_ERR_ARG;
     p.sf = *g.sample;
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
+  // wide kernels, fp32 residual epilogue: the output doubles as the target of TMA reductions (16-column blocks)
+  auto make_out_map = [&]() -> int {
+    p.resid_tma = g.epi == EPI_RESID && resid_tma && g.N % 4 == 0 && g.ldo % 4 == 0 && ((uintptr_t)g.out & 15) == 0;
+    if (!p.resid_tma) {
+      tmO = tmA;  // never dereferenced
+      return KW_OK;
+    }
+    return make_map_f32_sw64(&tmO, g.out, g.M, g.N, g.ldo);
+  };
   if (skinny) {  // decode-time shape: weights stream through the 128-row dimension, the batch is the MMA's N (64 or 128)
     const int bn = g.M <= 64 ? 64 : 128;
     // small projections: 32 weight rows per CTA tile -> 4x the CTAs in flight; 40 rows when 32-row tiles would spill
@@ -976,7 +1025,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     }
     const int tiles = ceil_div(g.M, 256) * ceil_div(g.N, BN);
     const int pairs = std::min(tiles, n_sm / 2);
-    gemm_tc2_kernel<<<2 * pairs, THREADS, c2::SMEM_BYTES, st>>>(tmA, tmB, p);
+    if ((rc = make_out_map())) return rc;
+    gemm_tc2_kernel<<<2 * pairs, THREADS, c2::SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
     KW_LAUNCH_OK();
     ++g_launches;
     return KW_OK;
@@ -987,7 +1037,8 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   if (rc) return rc;
   const int n_tiles = ceil_div(g.M, BM) * ceil_div(g.N, BN);
   const int grid = std::min(n_tiles, n_sm);
-  gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, p);
+  if ((rc = make_out_map())) return rc;
+  gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, tmO, p);
   KW_LAUNCH_OK();
   ++g_launches;
   return KW_OK;

@@ -61,6 +61,13 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap
       : "memory");
 }
 
+// x[tile] += smem tile, performed by the L2 (cp.reduce.async.bulk.tensor, element type and box from the tensor map);
+// completion is tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -258,15 +265,16 @@ struct MapKeyHash {
 
 // Encoded tensor maps are cached: workspaces and weights keep their addresses for the life of a model handle, so the
 // ~27 projections of every decode step hit the cache instead of calling into the driver.
-static inline int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* gdim,
-                                const cuuint64_t* gstride_bytes, const cuuint32_t* box, bool swizzle128 = true) {
+// key_code: 0 = bf16 unswizzled, 1 = bf16 128 B swizzle, 2 = fp32 64 B swizzle (reduction target of the residual epilogue)
+static inline int make_map_typed(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* gdim,
+                                 const cuuint64_t* gstride_bytes, const cuuint32_t* box, int key_code) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.ptr = ptr;
   key.rank = rank;
-  key.swizzle = swizzle128 ? 1 : 0;
+  key.swizzle = key_code;
   for (int i = 0; i < rank; ++i) { key.gdim[i] = gdim[i]; key.box[i] = box[i]; }
   for (int i = 0; i < rank - 1; ++i) key.gstride[i] = gstride_bytes[i];
   {
@@ -283,10 +291,11 @@ static inline int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, con
     return KW_ERR_CUDA;
   }
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstride_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = key_code == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = key_code == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : key_code == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(map, dt, rank, const_cast<void*>(ptr), gdim, gstride_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return KW_ERR_CUDA;
@@ -295,6 +304,19 @@ static inline int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, con
   if (cache.size() > 4096) cache.clear();
   cache[key] = *map;
   return KW_OK;
+}
+
+static inline int make_map_bf16(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* gdim,
+                                const cuuint64_t* gstride_bytes, const cuuint32_t* box, bool swizzle128 = true) {
+  return make_map_typed(map, ptr, rank, gdim, gstride_bytes, box, swizzle128 ? 1 : 0);
+}
+// fp32 [rows, cols] row-major, box = 16 columns (64 B) x 32 rows, 64 B swizzle: the block an epilogue warp hands to
+// cp.reduce.async.bulk.tensor (x += tile at the L2)
+static inline int make_map_f32_sw64(CUtensorMap* map, const void* ptr, int rows, int cols, int ld) {
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {16, 32};
+  return make_map_typed(map, ptr, 2, gdim, gstride, box, 2);
 }
 
 }  // namespace tc
