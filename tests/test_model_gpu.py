@@ -53,6 +53,31 @@ def test_tiny_fp32_matches_oracle_and_goldens(golden, name, arch):
     assert not a.is_cuda and torch.equal(a, b)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decoder_self_attention_over_long_histories(dtype):
+    """Raw logits at positions 0..299 (teacher-forced random history) against the oracle: the decode-time self-attention
+    walks its cache in 128-row chunks, so positions past 128 and 256 exercise the multi-chunk path."""
+    model, ref = build_pair(TINY, dtype, max_batch=4, oracle_weights="rounded" if dtype == torch.bfloat16 else "same")
+    mel = torch.from_numpy(logmel_batch_f64(clips("UG", 31), 128))
+    if dtype == torch.bfloat16:
+        mel = mel.to(torch.bfloat16).to(torch.float32)
+    model.encode(mel.cuda())
+    model.cross_kv(2)
+    g = torch.Generator().manual_seed(3)
+    toks = torch.randint(0, 50257, (2, 300), generator=g, dtype=torch.int32)
+    toks[:, 0] = 50258
+    with torch.no_grad():
+        enc_ref = ref.encode(mel)
+        cross = ref.cross_kv(enc_ref)
+        lg_ref = ref.logits(ref.decode(toks.long(), 0, [None] * TINY["decoder_layers"], cross))
+    tol = 1e-3 if dtype == torch.float32 else 5e-2   # bf16: rounding noise; an indexing bug is an O(1) error
+    td = toks.cuda()
+    for pos in range(300):
+        lg = model.step_logits(td, pos)
+        if pos in (0, 1, 31, 127, 128, 129, 200, 255, 256, 299):
+            assert _rel(lg.cpu(), lg_ref[:, pos]) <= tol, (pos, _rel(lg.cpu(), lg_ref[:, pos]))
+
+
 def test_tiny_errors_and_encoder_outputs():
     model, ref = build_pair(TINY, torch.float32, max_batch=4)
     mel = torch.from_numpy(logmel_batch_f64(clips("GS", 3), 128)).cuda()
