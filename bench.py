@@ -262,10 +262,10 @@ def ours(args, rank: int, world: int, local_rank: int):
     for _ in range(args.warmup):
         step_resident()
     if not args.no_stream:
-        # steady state before the timed region: a device batch in flight (so the first timed launch has a pass to
-        # interleave) and a buffer fill such that the K timed steps launch ceil(K / co) device batches — never fewer
+        # steady state before the timed region: device batches in flight (so the first timed launch has a pass to
+        # interleave and finished ids to hand back) and a buffer fill such that the K timed steps launch ceil(K / co) device batches — never fewer
         # encoder / decoder rows than K x 64 (an odd K at co = 2 does the work of K + 1 batches: counted against us)
-        while stream.device_batches < 2 or (stream.buffered + args.steps) % co != 0:
+        while stream.device_batches < 3 or (stream.buffered + args.steps) % co != 0:
             step_resident()
     # Timed region: only the dominant kernel category (encoder GEMMs) carries CUDA-event pairs; the other categories
     # are timed the same way in two extra, untimed steps right after (event pairs between the decode kernels would

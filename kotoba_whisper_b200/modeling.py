@@ -12,6 +12,7 @@ reference's path (run_pseudo_labelling.py:307-313 uses num_beams=1, greedy) and 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Union
 
@@ -544,8 +545,9 @@ class WhisperB200ForConditionalGeneration:
 
     def generate_stream(self, **generate_kwargs) -> "GenerateStream":
         """Throughput mode of the labelling loop (`for batch in loader: ids = model.generate(batch, **kw)`,
-        run_pseudo_labelling.py:333-341): `stream.submit(batch)` returns the ids of the PREVIOUS batch, `stream.flush()`
-        the last ones.  Same arguments and results as `generate`; see GenerateStream."""
+        run_pseudo_labelling.py:333-341): `stream.submit(batch)` returns the ids of the oldest finished batch (None while
+        the pipeline fills), `stream.flush()` the remaining ones, one batch per call.  Same arguments and results as
+        `generate`, plus `coalesce=k` (k submitted batches run as one device batch); see GenerateStream."""
         return GenerateStream(self, **generate_kwargs)
 
     # ---- teacher-forcing forward (distillation's frozen teacher) -----------------------------------------------------
@@ -662,6 +664,7 @@ class GenerateStream:
         self._plan = None
         self._buf: List[torch.Tensor] = []   # submitted batches waiting for their group to fill
         self._ready: List = []               # finished per-batch results, oldest first
+        self._late = None                    # (device batch, pinned token buffer, copy-done event): see _launch
         self.device_batches = 0              # device batches launched so far
 
     @property
@@ -716,8 +719,29 @@ class GenerateStream:
         self.device_batches += 1
         self._pending = (self._slot, mel, sizes)
         self._slot ^= 1
-        if prev is not None:
+        if prev is None:
+            return
+        if ts or os.environ.get("KW_STREAM_DEFER", "1") == "0":   # (KW_STREAM_DEFER=0: A/B measurements)
+            # a batch may need further seek passes on its own workspace, which the next launch reuses: finish it now
             self._finish(prev, tokens.cpu().numpy())
+            return
+        # Without timestamps a short-form batch is done after its first pass and only host work is left (strip, pack).
+        # Blocking on the tokens here would drain the stream at every device batch: the GPU would idle while the host
+        # packs the ids and enqueues the next batch.  The ids are instead copied to pinned memory behind an event and
+        # picked up at the NEXT launch, after that launch's kernels are queued (results come one device batch later).
+        host = torch.empty(tokens.shape, dtype=tokens.dtype, pin_memory=True)
+        with torch.cuda.device(m.device):
+            host.copy_(tokens, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(m.device))
+        late, self._late = self._late, (prev, host, done)
+        if late is not None:
+            self._finish_late(late)
+
+    def _finish_late(self, late):
+        prev, host, done = late
+        done.synchronize()
+        self._finish(prev, host.numpy())
 
     def submit(self, input_features: torch.Tensor):
         m, c = self.model, self.model.config
@@ -740,6 +764,9 @@ class GenerateStream:
         is empty (`while (ids := stream.flush()) is not None`).  With coalesce = 1 a single call returns the last batch."""
         if not self._ready and self._buf:
             self._launch()       # a group that did not fill: its own (smaller) device batch
+        if not self._ready and self._late is not None:
+            late, self._late = self._late, None
+            self._finish_late(late)
         if not self._ready and self._pending is not None:
             prev, self._pending = self._pending, None
             prompt, max_length, ts = self._plan
