@@ -303,6 +303,21 @@ def ours(args, rank: int, world: int, local_rank: int):
     lib.kw_profile_enable(0)
     passes = stats.get("passes", 0)
     ms_plain, _ = timed(step_plain, args.steps)   # same work batch by batch, for comparison with the stream
+    ms_stream1 = None
+    if co > 1:  # and the stream schedule without coalescing (one submitted batch per device batch), for the same comparison
+        stream1 = model.generate_stream(coalesce=1, **gen_kw)
+
+        def step_stream1():
+            ids1 = stream1.submit(fe.logmel_device(audio_dev))
+            if ids1 is not None:
+                prev, inflight["h"] = inflight["h"], gather.submit(ids1)
+                (prev or inflight["h"]).result()
+
+        for _ in range(4):
+            step_stream1()
+        ms_stream1, _ = timed(step_stream1, args.steps)
+        while (last := stream1.flush()) is not None:
+            gather.submit(last).result()
 
     def step_encoder_only():  # log-mel + encoder of one batch, no decode: what a stream step spends outside the decoder
         model.encode(fe.logmel_device(audio_dev), return_hidden=False)
@@ -443,7 +458,8 @@ def ours(args, rank: int, world: int, local_rank: int):
                        "slotted between the decoder positions of device batch i on one stream); per 64-clip step: 1 "
                        f"log-mel + encoder work for 64 clips + 1/{co} of a {co * BATCH}-row greedy pass + 1 token gather",
                        "coalesce": co, "device_batch": co * BATCH,
-                       "ms_per_step_batch_by_batch": ms_plain / args.steps, "l2": "inputs_larger_than_l2 (123 MB audio + 1.5 GB weights per step)",
+                       "ms_per_step_batch_by_batch": ms_plain / args.steps,
+                       "ms_per_step_stream_coalesce1": ms_stream1 / args.steps if ms_stream1 else None, "l2": "inputs_larger_than_l2 (123 MB audio + 1.5 GB weights per step)",
                        "tokens_out_shape": list(ids.shape)},
             "roofline": roofline, "roofline_extra": extra, "roofline_extra_note": f"timed with CUDA events in {extra_steps} extra steps after the timed region", "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": "audio_s/s", "ms_per_step": ms_e2e / args.steps,

@@ -67,7 +67,9 @@ __device__ __forceinline__ float ex2(float x) {
 // exponent field.  Inputs below -125 (masked keys: -inf) return ~2^-125 instead of 0; those keys meet all-zero V rows.
 // Measured on B200 (B=64, H=20, T=1500): never a win — 590 / 564 TFLOP/s against 609 at 25 % / 50 % offload on the earlier
 // 2-CTA kernel (latency-chain bound), 743 / 652 against 767 on this kernel (111 / 128 registers, no spills): a warp's own
-// instruction stream, not the shared MUFU, sets the length of its exp phase.  Compiled out by default.
+// instruction stream, not the shared MUFU, sets the length of its exp phase.  The packed fp32x2 form below (KW_ATT_POLY_PACKED,
+// 118 registers) brings the 25 % offload level with the plain kernel, 763.6 against 766.2 TFLOP/s, and no further
+// (profiles/r2_attention_poly_variants.txt).  Compiled out by default.
 #ifndef KW_ATT_POLY_PAIRS
 #define KW_ATT_POLY_PAIRS 0  // pairs out of every 4 (8 scores) whose exp2 runs on the FMA pipe
 #endif
@@ -80,7 +82,26 @@ __device__ __forceinline__ float ex2_poly(float x) {  // scalar form: every cons
   q = fmaf(q, f, 0.9999281167984009f);
   return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
 }
+#ifndef KW_ATT_POLY_PACKED
+#define KW_ATT_POLY_PACKED 0
+#endif
+#if KW_ATT_POLY_PACKED
+// the same arithmetic on the packed fp32x2 pipe: 2 FMNMX + 2 FADD2 + 4 FFMA2 + 2 (shift + add) per PAIR instead of 9 scalar
+// operations per element
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x = make_float2(fmaxf(x.x, -125.0f), fmaxf(x.y, -125.0f));
+  const float2 M = make_float2(12582912.0f, 12582912.0f), NM = make_float2(-12582912.0f, -12582912.0f);
+  const float2 t = __fadd2_rn(x, M);
+  const float2 f = __ffma2_rn(__fadd2_rn(t, NM), make_float2(-1.0f, -1.0f), x);
+  float2 q = __ffma2_rn(make_float2(0.05517125502228737f, 0.05517125502228737f), f, make_float2(0.2426103800535202f, 0.2426103800535202f));
+  q = __ffma2_rn(q, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  q = __ffma2_rn(q, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+#else
 __device__ __forceinline__ float2 ex2_poly2(float2 x) { return make_float2(ex2_poly(x.x), ex2_poly(x.y)); }
+#endif
 // Measured and dropped in round 2: skipping the exp2 work of query rows past Tq (a warp of the last 128-row tile) and of
 // the key groups past Tk in the last key tile (4.4 % of the MUFU work in total): 760 / 666 TFLOP/s against 767 — the
 // extra control flow costs registers (109 / 128 against 106) and scheduling freedom in the loop that matters.
