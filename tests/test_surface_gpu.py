@@ -308,6 +308,22 @@ def test_generate_stream_coalesce_equals_batch_by_batch(dtype, ts):
         stream.submit(torch.zeros((9, 128, 3000), device="cuda:0"))   # > max_batch
     with pytest.raises(ValueError):
         model.generate_stream(coalesce=0, **kw)
+    # a group that never fills (one batch, then flush) and `return_segments=True` (dict per submitted batch, as generate)
+    stream = model.generate_stream(coalesce=3, return_segments=True, **kw)
+    assert stream.submit(batches[2]) is None and stream.buffered == 1 and stream.device_batches == 0
+    r = stream.flush()
+    ref = model.generate(batches[2], return_segments=True, **kw)
+    assert torch.equal(r["sequences"].cpu(), ref["sequences"].cpu()) and r["segments"] == ref["segments"]
+    assert stream.flush() is None
+    stream = model.generate_stream(coalesce=2, return_segments=True, **kw)
+    got = [stream.submit(b) for b in batches[:4]]
+    got = [r for r in got if r is not None]
+    while (r := stream.flush()) is not None:
+        got.append(r)
+    assert len(got) == 4
+    for r, b in zip(got, batches[:4]):
+        ref = model.generate(b, return_segments=True, **kw)
+        assert torch.equal(r["sequences"].cpu(), ref["sequences"].cpu()) and r["segments"] == ref["segments"]
 
 
 def test_kotoba_bf16_coalesced_128_row_decode_is_row_identical():
