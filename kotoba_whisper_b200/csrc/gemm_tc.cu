@@ -46,6 +46,7 @@ struct Params {
   int M, N, K, ldo, pos_period, epi, out_bf16;
   SampleFuse sf;  // EPI_ARGMAX (decode-time vocabulary projection)
   int w_hint;  // skinny kernel: L2 eviction priority of the weight loads (GemmArgs::w_hint)
+  int store_tma;  // wide kernels, bf16 outputs: 32 x 32 blocks leave through TMA stores instead of per-thread 16-byte stores
   int resid_tma;  // wide kernels, EPI_RESID: 1 = x += tile as a TMA reduction at the L2, 0 = read-modify-write by the epilogue warps
 };
 
@@ -205,7 +206,8 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
       if (cc + XDEPTH < NCH) load_resid(cc + XDEPTH, xr[cc % XDEPTH]);  // refill the slot just consumed
       continue;
     }
-    if (row_ok) {
+    const bool tma_st = p.out_bf16 && p.store_tma;  // warp-uniform; rows >= M are computed too and clipped by the tensor map
+    if (row_ok || tma_st) {
       {
         const float4* b4p = reinterpret_cast<const float4*>(s_bias_stage + c * 16);
 #pragma unroll
@@ -235,7 +237,28 @@ __device__ __forceinline__ void epilogue_tile(const Params& p, const CUtensorMap
           v[j] += q4.x; v[j + 1] += q4.y; v[j + 2] += q4.z; v[j + 3] += q4.w;
         }
       }
-      if (p.out_bf16) {
+      if (tma_st) {
+        // two 16-column chunks make one 32 x 32 bf16 block (64 B per row, the tensor map's 64 B swizzle) -> one TMA store
+        const int half = cc & 1, sw = (lane >> 1) & 3;
+        if (half == 0) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous block has left smem
+          __syncwarp();
+        }
+        char* blk = reinterpret_cast<char*>(s_stage) + lane * 64;
+        uint4 w0, w1;
+        w0.x = pack_bf16(v[0], v[1]); w0.y = pack_bf16(v[2], v[3]); w0.z = pack_bf16(v[4], v[5]); w0.w = pack_bf16(v[6], v[7]);
+        w1.x = pack_bf16(v[8], v[9]); w1.y = pack_bf16(v[10], v[11]); w1.z = pack_bf16(v[12], v[13]); w1.w = pack_bf16(v[14], v[15]);
+        *reinterpret_cast<uint4*>(blk + (((2 * half) ^ sw) << 4)) = w0;
+        *reinterpret_cast<uint4*>(blk + (((2 * half + 1) ^ sw) << 4)) = w1;
+        if (half == 1) {  // N % 32 == 0 for the wide kernels: chunks always come in pairs
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tmO, smem_u32(s_stage), col0 - 16, m0 + quarter * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else if (p.out_bf16) {
         bf16* o = reinterpret_cast<bf16*>(p.out) + (size_t)row * p.ldo + col0;
 #pragma unroll
         for (int j = 0; j < 16; j += 8) {
@@ -933,6 +956,11 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
     return e ? atoi(e) : 1;
   }();
   p.resid_tma = 0;
+  p.store_tma = 0;
+  static const int store_tma = [] {  // KW_STORE_TMA=0: per-thread stores of the bf16 epilogues (A/B measurements)
+    const char* e = getenv("KW_STORE_TMA");
+    return e ? atoi(e) : 1;
+  }();
   if (g.epi == EPI_ARGMAX) {
     if (!g.sample || !(g.M <= sk::MAX_BN) || g.N <= 8192) return KW_ERR_UNSUPPORTED;  // R = 128 decode-time kernel only
     if (g.sample->tail0 % 32 != 0 || g.sample->n_part != 2 * ceil_div(g.sample->tail0, 128) || g.sample->tail0 > g.N ||
@@ -944,11 +972,12 @@ int gemm_tc(const GemmArgs& g, cudaStream_t st) {
   // wide kernels, fp32 residual epilogue: the output doubles as the target of TMA reductions (16-column blocks)
   auto make_out_map = [&]() -> int {
     p.resid_tma = g.epi == EPI_RESID && resid_tma && g.N % 4 == 0 && g.ldo % 4 == 0 && ((uintptr_t)g.out & 15) == 0;
-    if (!p.resid_tma) {
-      tmO = tmA;  // never dereferenced
-      return KW_OK;
-    }
-    return make_map_f32_sw64(&tmO, g.out, g.M, g.N, g.ldo);
+    if (p.resid_tma) return make_map_f32_sw64(&tmO, g.out, g.M, g.N, g.ldo);
+    p.store_tma = store_tma && g.out_type == KW_BF16 && (g.epi == EPI_STORE || g.epi == EPI_GELU) && g.N % 32 == 0 &&
+                  g.ldo % 8 == 0 && ((uintptr_t)g.out & 15) == 0;
+    if (p.store_tma) return make_map_bf16_sw64(&tmO, g.out, g.M, g.N, g.ldo);
+    tmO = tmA;  // never dereferenced
+    return KW_OK;
   };
   if (skinny) {  // decode-time shape: weights stream through the 128-row dimension, the batch is the MMA's N (64 or 128)
     const int bn = g.M <= 64 ? 64 : 128;

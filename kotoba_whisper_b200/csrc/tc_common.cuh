@@ -68,6 +68,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -265,7 +270,8 @@ struct MapKeyHash {
 
 // Encoded tensor maps are cached: workspaces and weights keep their addresses for the life of a model handle, so the
 // ~27 projections of every decode step hit the cache instead of calling into the driver.
-// key_code: 0 = bf16 unswizzled, 1 = bf16 128 B swizzle, 2 = fp32 64 B swizzle (reduction target of the residual epilogue)
+// key_code: 0 = bf16 unswizzled, 1 = bf16 128 B swizzle, 2 = fp32 64 B swizzle (reduction target of the residual epilogue),
+// 3 = bf16 64 B swizzle (TMA-store target of the bf16 epilogues)
 static inline int make_map_typed(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* gdim,
                                  const cuuint64_t* gstride_bytes, const cuuint32_t* box, int key_code) {
   static std::mutex mu;
@@ -292,7 +298,7 @@ static inline int make_map_typed(CUtensorMap* map, const void* ptr, int rank, co
   }
   cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapDataType dt = key_code == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  const CUtensorMapSwizzle sw = key_code == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+  const CUtensorMapSwizzle sw = key_code >= 2 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : key_code == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = enc(map, dt, rank, const_cast<void*>(ptr), gdim, gstride_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -317,6 +323,13 @@ static inline int make_map_f32_sw64(CUtensorMap* map, const void* ptr, int rows,
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {16, 32};
   return make_map_typed(map, ptr, 2, gdim, gstride, box, 2);
+}
+// bf16 [rows, cols] row-major, box = 32 columns (64 B) x 32 rows, 64 B swizzle: TMA-store target of the bf16 epilogues
+static inline int make_map_bf16_sw64(CUtensorMap* map, const void* ptr, int rows, int cols, int ld) {
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  return make_map_typed(map, ptr, 2, gdim, gstride, box, 3);
 }
 
 }  // namespace tc
