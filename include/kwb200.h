@@ -170,7 +170,11 @@ int kw_decode_step(kw_model* m, int32_t* tokens, int32_t ld_tokens, int32_t B, i
  * cross K/V, prefill of `n_prompt` prompt tokens (host array), then greedy steps until every row has emitted eos or
  * the sequence length reaches max_length.  tokens dev i32 [B, max_length] receives prompt + generated ids (pad after
  * eos).  Synchronises the stream every `check_every` steps to test the all-finished flag (0 = never, run to
- * max_length).  Returns the number of decoder positions evaluated (>= 0) or a negative kw_status. */
+ * max_length).  Returns the number of decoder positions evaluated (>= 0) or a negative kw_status.
+ * B <= max_batch.  The bf16 decode-time kernels take up to 128 rows per launch (the batch is the N of the weight-streaming
+ * tcgen05 GEMMs: 64- and 128-wide instantiations); a position costs nearly the same for 128 rows as for 64 outside the
+ * cross-attention K/V stream, which is why the host side coalesces two 64-utterance batches into one 128-row pass
+ * (GenerateStream(coalesce=2)).  A row's ids do not depend on the batch it is decoded in. */
 int kw_greedy_pass(kw_model* m, int32_t B, const int32_t* prompt, int32_t n_prompt, int32_t max_length,
                    int32_t return_timestamps, int32_t check_every, int32_t* tokens, kw_stream stream);
 
